@@ -1,0 +1,170 @@
+/*
+ * qagnn_b200 — C ABI of the B200-native QA-GNN message-passing path.
+ *
+ * The reference (michiyasunaga/qagnn) has no FFI layer: its operator API for this path is the
+ * Python nn.Module surface in modeling/modeling_qagnn.py.  This header is the boundary a
+ * maintainer binds (ctypes stub in INTEGRATION.md) to replace, one-for-one:
+ *
+ *   qagnn_graph_prep          <- the index work of GATConvE.forward     modeling_qagnn.py:419-438
+ *                                + the out-degree count of message()     modeling_qagnn.py:476-479
+ *   qagnn_fold_weights        <- edge_encoder on one-hots :30,:433; BatchNorm(eval) :30,:408;
+ *                                linear_key/linear_msg/linear_query weight views :401-403,:464-466
+ *   qagnn_gatconve_forward    <- GATConvE.forward / GATConvE.message      modeling_qagnn.py:411-484
+ *                                (+ torch_geometric propagate/softmax, torch_scatter scatter)
+ *   qagnn_node_feature_extra  <- QAGNN_Message_Passing.forward prologue   modeling_qagnn.py:62-73,86
+ *   qagnn_mp_forward          <- QAGNN_Message_Passing.forward            modeling_qagnn.py:53-95
+ *                                (mp_helper :45-50, Vh/Vx epilogue :92)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns every
+ *     buffer (inputs, outputs, workspaces); the library never allocates, frees or retains them;
+ *   - sizes of the opaque workspaces come from the *_bytes() queries; buffers must be 256-byte
+ *     aligned (torch allocations are);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are re-entrant per
+ *     stream and asynchronous, except qagnn_graph_prep with validate != 0, which synchronises the
+ *     stream once to report out-of-range indices;
+ *   - return value: 0 = ok, negative = error (qagnn_status_string).  No C++ exceptions cross
+ *     the boundary;
+ *   - dtypes: features fp32 row-major, indices int64 exactly as the reference's loader
+ *     (utils/data_utils.py:79-197) produces them.  Eval-mode forward only (dropout = identity,
+ *     BatchNorm running statistics), which is the reference's evaluate_accuracy path (qagnn.py:30-38).
+ */
+#ifndef QAGNN_B200_H_
+#define QAGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QAGNN_ABI_VERSION 1
+
+enum {
+  QAGNN_OK = 0,
+  QAGNN_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, D % H != 0, ... */
+  QAGNN_ERR_CUDA = -2,             /* a launch or runtime call failed; see qagnn_last_cuda_error */
+  QAGNN_ERR_INDEX_RANGE = -3,      /* edge_index / edge_type / node_type outside its range */
+  QAGNN_ERR_WORKSPACE = -4,        /* caller-provided workspace is too small */
+  QAGNN_ERR_UNSUPPORTED = -5       /* shape outside what the kernels are instantiated for */
+};
+
+/* Problem shape.  N nodes in the batched graph, E real directed edges (self loops excluded; the
+ * library appends the N self loops itself, modeling_qagnn.py:436-438), D = emb_dim, H = head_count
+ * (modeling_qagnn.py:387), T = n_ntype, R = n_etype, k = number of GATConvE layers,
+ * n_per_graph = nodes per sub-graph when the batch is made of equal-sized sub-graphs laid out
+ * back to back as LM_QAGNN.batch_graph does (modeling_qagnn.py:244-251), else 0 (unknown). */
+typedef struct qagnn_shape {
+  int64_t N;
+  int64_t E;
+  int32_t D;
+  int32_t H;
+  int32_t T;
+  int32_t R;
+  int32_t k;
+  int32_t n_per_graph;
+} qagnn_shape;
+
+/* Raw parameters, in the reference's own layout (row-major [out, in], fp32), i.e. pointers into
+ * the tensors of the module's state_dict. */
+typedef struct qagnn_edge_encoder_params { /* modeling_qagnn.py:30 */
+  const float *lin0_w, *lin0_b;            /* [D, R+1+2T], [D]  edge_encoder.0 */
+  const float *bn_w, *bn_b, *bn_mean, *bn_var; /* [D] each     edge_encoder.1 */
+  const float *lin3_w, *lin3_b;            /* [D, D], [D]      edge_encoder.3 */
+} qagnn_edge_encoder_params;
+
+typedef struct qagnn_layer_params { /* GATConvE, modeling_qagnn.py:401-408 */
+  const float *key_w, *key_b;       /* [D, 3D], [D] linear_key   */
+  const float *msg_w, *msg_b;       /* [D, 3D], [D] linear_msg   */
+  const float *query_w, *query_b;   /* [D, 2D], [D] linear_query */
+  const float *mlp0_w, *mlp0_b;     /* [D, D], [D]  mlp.0 */
+  const float *bn_w, *bn_b, *bn_mean, *bn_var; /* [D] each mlp.1 */
+  const float *mlp3_w, *mlp3_b;     /* [D, D], [D]  mlp.3 */
+} qagnn_layer_params;
+
+typedef struct qagnn_mp_params { /* QAGNN_Message_Passing, modeling_qagnn.py:19-38 */
+  const float *emb_node_type_w, *emb_node_type_b; /* [D/2, T], [D/2]   */
+  const float *emb_score_w, *emb_score_b;         /* [D/2, D/2], [D/2] */
+  const float *vh_w, *vh_b, *vx_w, *vx_b;         /* [D, D], [D] each  */
+  const float *score_basis;                       /* [D/2] = float32 pow(1.1, j), modeling_qagnn.py:70-71 */
+} qagnn_mp_params;
+
+int32_t qagnn_abi_version(void);
+const char *qagnn_status_string(int32_t status);
+/* cudaError_t of the most recent QAGNN_ERR_CUDA on this thread, as text. */
+const char *qagnn_last_cuda_error(void);
+
+/* ---- graph prep (once per forward, shared by all k layers) ------------------------------- */
+
+/* Byte offsets of the arrays inside the opaque prep workspace (for inspection / tests).
+ * E' = E + N.  All arrays are int32. */
+typedef struct qagnn_prep_layout {
+  size_t total_bytes;
+  size_t src;          /* [E'] source of edge e (self loops at e >= E)                */
+  size_t tgt;          /* [E'] target of edge e                                       */
+  size_t combo;        /* [E'] (etype'*T + type[src])*T + type[tgt], etype' = R on self loops */
+  size_t rowptr_src;   /* [N+1] CSR by source; out-degree = rowptr_src[v+1]-rowptr_src[v] */
+  size_t rowptr_tgt;   /* [N+1] CSR by target                                         */
+  size_t perm_src;     /* [E'] edge ids stably sorted by source                        */
+  size_t perm_tgt;     /* [E'] edge ids stably sorted by target                        */
+  size_t csr_src_tgt;  /* [E'] tgt[perm_src[p]]                                       */
+  size_t csr_src_combo;/* [E'] combo[perm_src[p]]                                     */
+  size_t csr_tgt_src;  /* [E'] src[perm_tgt[p]]                                       */
+  size_t csr_tgt_combo;/* [E'] combo[perm_tgt[p]]                                     */
+  size_t csr_tgt_apos; /* [E'] position of edge perm_tgt[p] in the by-source order      */
+  size_t status;       /* [4]  device-side error word + counters                        */
+  size_t scratch;      /* internal                                                     */
+} qagnn_prep_layout;
+
+int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layout *out_host);
+size_t qagnn_graph_prep_bytes(int64_t N, int64_t E);
+
+/* edge_index int64 [2,E] (row 0 = source, row 1 = target), edge_type int64 [E] in [0,R),
+ * node_type int64 [N] in [0,T).  validate != 0: synchronise `stream` and return
+ * QAGNN_ERR_INDEX_RANGE if any index is out of range (the kernels clamp, never fault). */
+int32_t qagnn_graph_prep(const int64_t *edge_index, const int64_t *edge_type, const int64_t *node_type,
+                         const qagnn_shape *shape, void *prep, size_t prep_bytes, int32_t validate,
+                         void *stream);
+
+/* ---- weight folding (once per set of weights) --------------------------------------------- */
+
+size_t qagnn_fold_bytes(const qagnn_shape *shape);
+/* `layers_host` is a HOST array of shape->k structs holding DEVICE pointers; `mp_host` may be NULL
+ * when only qagnn_gatconve_forward will be used. */
+int32_t qagnn_fold_weights(const qagnn_shape *shape, const qagnn_edge_encoder_params *edge_encoder_host,
+                           const qagnn_layer_params *layers_host, const qagnn_mp_params *mp_host,
+                           void *folded, size_t folded_bytes, void *stream);
+
+/* ---- forward ----------------------------------------------------------------------------------- */
+
+size_t qagnn_forward_workspace_bytes(const qagnn_shape *shape);
+
+/* One GATConvE layer `layer` (0-based index into the folded blob):
+ *   out[N,D] = mlp(propagate(...))   (NO GELU: that is applied by mp_helper, modeling_qagnn.py:48)
+ * alpha_out (optional, may be NULL): [E+N, H] softmax weights BEFORE the out-degree rescale, in
+ * edge_index' order (real edges, then self loops) — what return_attention_weights=True returns.
+ * aggr_out (optional): [N,D] propagate() output before the node MLP. */
+int32_t qagnn_gatconve_forward(const qagnn_shape *shape, int32_t layer, const float *x, const float *extra,
+                               const void *prep, const void *folded, float *out, float *alpha_out,
+                               float *aggr_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* node_feature_extra[N,D] = [GELU(emb_node_type(onehot(type))) ‖ GELU(emb_score(sin(basis*score)))] */
+int32_t qagnn_node_feature_extra(const qagnn_shape *shape, const int64_t *node_type, const float *node_score,
+                                 const void *folded, float *extra_out, void *workspace, size_t workspace_bytes,
+                                 void *stream);
+
+/* Whole QAGNN_Message_Passing.forward (eval): H_in [N,D], node_type int64 [N], node_score [N],
+ * out [N,D] = GELU(Vh(H_in) + Vx(X_k)).  x_layers_out (optional): [k,N,D] activations after each
+ * layer's GELU. */
+int32_t qagnn_mp_forward(const qagnn_shape *shape, const float *H_in, const int64_t *node_type,
+                         const float *node_score, const void *prep, const void *folded, float *out,
+                         float *x_layers_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Launch counters since load (kernels this library enqueued); for bench.py's gpu_launches. */
+int64_t qagnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAGNN_B200_H_ */

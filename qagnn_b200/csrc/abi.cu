@@ -1,0 +1,179 @@
+// extern "C" entry points declared in include/qagnn_b200.h: the forward orchestration of
+// GATConvE (modeling/modeling_qagnn.py:411-484) and QAGNN_Message_Passing (modeling_qagnn.py:53-95).
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace qagnn {
+
+static std::atomic<long long> g_launches{0};
+static thread_local char g_cuda_err[256] = "";
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int32_t cuda_fail(cudaError_t e) {
+  strncpy(g_cuda_err, cudaGetErrorString(e), sizeof(g_cuda_err) - 1);
+  return QAGNN_ERR_CUDA;
+}
+
+WorkLayout make_work_layout(const qagnn_shape& s) {
+  WorkLayout W;
+  const size_t N = (size_t)s.N, D = (size_t)s.D, Ep = (size_t)(s.N + s.E), H = (size_t)s.H;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n * 4) / 4; return r; };
+  W.qkm = take(N * 3 * D);
+  W.aggr = take(N * D);
+  W.hmid = take(N * D);
+  W.xa = take(N * D);
+  W.xb = take(N * D);
+  W.extra = take(N * D);
+  W.sinb = take(N * (D / 2));
+  W.score = take(Ep * H);
+  W.alpha = take(Ep * H);
+  W.total = o;
+  return W;
+}
+
+namespace {
+
+__global__ void node_feature_prologue_kernel(int64_t N, int D, int T, const int64_t* __restrict__ node_type,
+                                             const float* __restrict__ node_score, const float* __restrict__ type_tab,
+                                             const float* __restrict__ basis, float* __restrict__ extra,
+                                             float* __restrict__ sinb) {
+  // extra[v, :D/2] = GELU(emb_node_type(onehot(type)))  == row `type` of the folded table (:65-66)
+  // sinb[v, j]     = sin(1.1^j * score[v])                                                (:70-72)
+  const int Dh = D / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * Dh; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / Dh;
+    const int j = (int)(i % Dh);
+    int64_t t = node_type[v];
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+    extra[v * D + j] = type_tab[t * Dh + j];
+    sinb[i] = sinf(basis[j] * node_score[v]);  // precise sinf: arguments reach ~1e4 * |score|
+  }
+}
+
+int32_t check_shape_fwd(const qagnn_shape* s) {
+  if (!s) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (s->N <= 0 || s->E < 0 || s->D <= 0 || s->H <= 0 || s->T <= 0 || s->R <= 0 || s->k < 0)
+    return QAGNN_ERR_INVALID_ARGUMENT;
+  if (s->D % s->H != 0 || s->D % 2 != 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (s->N + s->E >= (int64_t)1 << 31) return QAGNN_ERR_INVALID_ARGUMENT;
+  return QAGNN_OK;
+}
+
+// one GATConvE layer; `final_act` = ACT_NONE for the bare layer, ACT_GELU when called from mp_helper
+int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, int layer, const float* x,
+                      const float* extra, const void* prep, const qagnn_prep_layout& pl, const float* folded,
+                      float* out, float* alpha_out, float* aggr_out, float* ws, Act final_act, cudaStream_t st) {
+  const int D = s.D;
+  const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
+  float* qkm = ws + W.qkm;
+  float* aggr = aggr_out ? aggr_out : ws + W.aggr;
+  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                        (:440, :464-466 node part, :469)
+  QAGNN_RETURN_IF(sgemm_tn(x, D, D, extra, D, D, lb + L.wp, 2 * D, lb + L.bp, qkm, 3 * D, s.N, 3 * D, ACT_NONE, st));
+  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
+  QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
+                                         ws + W.alpha, aggr, alpha_out, st));
+  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
+  QAGNN_RETURN_IF(sgemm_tn(aggr, D, D, nullptr, 0, 0, lb + L.w1, D, lb + L.b1, ws + W.hmid, D, s.N, D, ACT_RELU, st));
+  QAGNN_RETURN_IF(sgemm_tn(ws + W.hmid, D, D, nullptr, 0, 0, lb + L.w2, D, lb + L.b2, out, D, s.N, D, final_act, st));
+  return QAGNN_OK;
+}
+
+int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, const int64_t* node_type,
+                      const float* node_score, const float* folded, float* extra, float* ws, cudaStream_t st) {
+  const int D = s.D, Dh = D / 2;
+  const int64_t n = s.N * Dh;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  node_feature_prologue_kernel<<<(unsigned)g, 256, 0, st>>>(s.N, D, s.T, node_type, node_score, folded + L.type_tab,
+                                                            folded + L.basis, extra, ws + W.sinb);
+  QAGNN_CHECK_LAUNCH();
+  // extra[:, D/2:] = GELU(emb_score(sinb))                                  (:73)
+  return sgemm_tn(ws + W.sinb, Dh, Dh, nullptr, 0, 0, folded + L.ws, Dh, folded + L.bs, extra + Dh, D, s.N, Dh,
+                  ACT_GELU, st);
+}
+
+}  // namespace
+}  // namespace qagnn
+
+using namespace qagnn;
+
+extern "C" int32_t qagnn_abi_version(void) { return QAGNN_ABI_VERSION; }
+
+extern "C" const char* qagnn_status_string(int32_t status) {
+  switch (status) {
+    case QAGNN_OK: return "ok";
+    case QAGNN_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case QAGNN_ERR_CUDA: return "CUDA error";
+    case QAGNN_ERR_INDEX_RANGE: return "index out of range in edge_index / edge_type / node_type";
+    case QAGNN_ERR_WORKSPACE: return "workspace too small";
+    case QAGNN_ERR_UNSUPPORTED: return "unsupported shape";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* qagnn_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int64_t qagnn_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t qagnn_forward_workspace_bytes(const qagnn_shape* shape) {
+  if (check_shape_fwd(shape) != QAGNN_OK) return 0;
+  return align_up(make_work_layout(*shape).total * sizeof(float));
+}
+
+extern "C" int32_t qagnn_gatconve_forward(const qagnn_shape* shape, int32_t layer, const float* x, const float* extra,
+                                          const void* prep, const void* folded, float* out, float* alpha_out,
+                                          float* aggr_out, void* workspace, size_t workspace_bytes, void* stream) {
+  QAGNN_RETURN_IF(check_shape_fwd(shape));
+  if (!x || !extra || !prep || !folded || !out || !workspace) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (layer < 0 || layer >= shape->k) return QAGNN_ERR_INVALID_ARGUMENT;
+  const FoldLayout L = make_fold_layout(*shape);
+  const WorkLayout W = make_work_layout(*shape);
+  if (workspace_bytes < W.total * sizeof(float)) return QAGNN_ERR_WORKSPACE;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(shape->N, shape->E, &pl));
+  return layer_forward(*shape, L, W, layer, x, extra, prep, pl, (const float*)folded, out, alpha_out, aggr_out,
+                       (float*)workspace, ACT_NONE, (cudaStream_t)stream);
+}
+
+extern "C" int32_t qagnn_node_feature_extra(const qagnn_shape* shape, const int64_t* node_type, const float* node_score,
+                                            const void* folded, float* extra_out, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  QAGNN_RETURN_IF(check_shape_fwd(shape));
+  if (!node_type || !node_score || !folded || !extra_out || !workspace) return QAGNN_ERR_INVALID_ARGUMENT;
+  const FoldLayout L = make_fold_layout(*shape);
+  const WorkLayout W = make_work_layout(*shape);
+  if (workspace_bytes < W.total * sizeof(float)) return QAGNN_ERR_WORKSPACE;
+  return extra_forward(*shape, L, W, node_type, node_score, (const float*)folded, extra_out, (float*)workspace,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in, const int64_t* node_type,
+                                    const float* node_score, const void* prep, const void* folded, float* out,
+                                    float* x_layers_out, void* workspace, size_t workspace_bytes, void* stream) {
+  QAGNN_RETURN_IF(check_shape_fwd(shape));
+  if (!H_in || !node_type || !node_score || !prep || !folded || !out || !workspace) return QAGNN_ERR_INVALID_ARGUMENT;
+  const qagnn_shape& s = *shape;
+  const FoldLayout L = make_fold_layout(s);
+  const WorkLayout W = make_work_layout(s);
+  if (workspace_bytes < W.total * sizeof(float)) return QAGNN_ERR_WORKSPACE;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(s.N, s.E, &pl));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  const float* f = (const float*)folded;
+  float* extra = ws + W.extra;
+  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, extra, ws, st));
+  const size_t ND = (size_t)s.N * s.D;
+  const float* x = H_in;
+  for (int l = 0; l < s.k; ++l) {  // mp_helper, :45-50 (dropout is the identity in eval)
+    float* xo = x_layers_out ? x_layers_out + (size_t)l * ND : ws + ((l & 1) ? W.xb : W.xa);
+    QAGNN_RETURN_IF(layer_forward(s, L, W, l, x, extra, prep, pl, f, xo, nullptr, nullptr, ws, ACT_GELU, st));
+    x = xo;
+  }
+  // output = GELU(Vh(H) + Vx(X))                                             (:92)
+  return sgemm_tn(H_in, s.D, s.D, x, s.D, s.D, f + L.vcat, 2 * s.D, f + L.vbias, out, s.D, s.N, s.D, ACT_GELU, st);
+}

@@ -1,0 +1,97 @@
+// Shared declarations for the qagnn_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/qagnn_b200.h"
+
+namespace qagnn {
+
+constexpr size_t kAlign = 256;
+__host__ __device__ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// ---- launch bookkeeping -------------------------------------------------------------------------
+void note_launch(int n = 1);
+int32_t cuda_fail(cudaError_t e);  // records the error text, returns QAGNN_ERR_CUDA
+
+#define QAGNN_CHECK_LAUNCH()                               \
+  do {                                                     \
+    cudaError_t e__ = cudaGetLastError();                  \
+    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__);\
+    ::qagnn::note_launch();                                \
+  } while (0)
+
+#define QAGNN_CHECK_CUDA(expr)                              \
+  do {                                                     \
+    cudaError_t e__ = (expr);                              \
+    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__);\
+  } while (0)
+
+#define QAGNN_RETURN_IF(st)        \
+  do {                             \
+    int32_t s__ = (st);            \
+    if (s__ != QAGNN_OK) return s__; \
+  } while (0)
+
+// ---- folded-weight blob ---------------------------------------------------------------------------
+// All offsets in floats from the start of the blob.  C = (R+1)*T*T rows in the edge tables.
+struct FoldLayout {
+  int D, H, T, R, k, C;
+  size_t tab;        // [C, D]   edge_encoder(onehot(c))                      (layer-invariant)
+  size_t hidden;     // [C, D]   scratch: ReLU(BN(lin0(onehot)))
+  size_t type_tab;   // [T, D/2] GELU(emb_node_type(onehot(t)))
+  size_t basis;      // [D/2]    copy of score_basis
+  size_t ws;         // [D/2, D/2] emb_score.weight   (copy)
+  size_t bs;         // [D/2]
+  size_t vcat;       // [D, 2D]  [Vh | Vx]
+  size_t vbias;      // [D]      Vh.bias + Vx.bias
+  size_t layer0;     // per-layer block start
+  size_t layer_stride;
+  // per-layer offsets relative to the layer block
+  size_t wp;         // [3D, 2D] rows: W_q/sqrt(d) ; W_k[:, :2D] ; W_m[:, :2D]
+  size_t bp;         // [3D]     b_q/sqrt(d) ; 0 ; 0
+  size_t ke;         // [C, D]   tab @ W_k[:, 2D:]^T + b_k
+  size_t me;         // [C, D]   tab @ W_m[:, 2D:]^T + b_m
+  size_t w1;         // [D, D]   BN-folded mlp.0
+  size_t b1;         // [D]
+  size_t w2;         // [D, D]   mlp.3 (copy)
+  size_t b2;         // [D]
+  size_t total;      // floats
+};
+FoldLayout make_fold_layout(const qagnn_shape& s);
+
+// ---- forward workspace ------------------------------------------------------------------------------
+struct WorkLayout {
+  size_t qkm;     // [N, 3D]
+  size_t aggr;    // [N, D]
+  size_t hmid;    // [N, D]
+  size_t xa, xb;  // [N, D] ping-pong layer activations
+  size_t extra;   // [N, D]
+  size_t sinb;    // [N, D/2]
+  size_t score;   // [E', H]  raw logits / exp scratch (by-source order)
+  size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order)
+  size_t total;   // floats
+};
+WorkLayout make_work_layout(const qagnn_shape& s);
+
+// ---- kernels' host launchers (each returns a status) ------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// C[M,N] (ldc) = act( [A1 | A2] @ W^T + bias ),  A1 [M,K1] (lda1), A2 [M,K2] (lda2) or null,
+// W [N, K1+K2] row-major (ldw).  bias may be null.
+int32_t sgemm_tn(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* W, int ldw,
+                 const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st);
+
+int32_t launch_message_passing(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
+                               const float* qkm, const float* ke, const float* me, float* score, float* alpha,
+                               float* aggr, float* alpha_out, cudaStream_t st);
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // utils/layers.py:10-14
+  const float k0 = 0.7978845608028654f;  // sqrt(2/pi)
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + 0.044715f * x * x * x)));
+}
+
+}  // namespace qagnn

@@ -1,0 +1,308 @@
+// Graph prep: the layer-invariant index work of GATConvE (modeling/modeling_qagnn.py:419-438,
+// 476-479), done once per forward and reused by all k layers.
+//
+//   edge_index' = [edge_index | self loops]                                   (:436-438)
+//   combo[e]    = (etype'[e]*T + type[src])*T + type[tgt]   — the position of the single 1-triple
+//                 in the reference's [E', R+1+2T] one-hot edge feature         (:419-432)
+//   out-degree by source (self loop included)                                  (:476-479)
+//   stable CSR orders by source (softmax groups, :472) and by target (aggregation, :442)
+//
+// Everything is deterministic: the atomics only count, segment order is restored by an in-segment
+// sort on the edge id, so the downstream floating-point sums are run-to-run reproducible.
+#include "common.cuh"
+
+namespace qagnn {
+
+namespace {
+
+struct PrepScratch {
+  size_t cnt_src, cnt_tgt;  // [N] each (also reused as fill cursors after the scan)
+  size_t bsum;              // [2 * nb]
+  size_t tmp_src, tmp_tgt;  // [E'] unsorted CSR fill
+  size_t inv_src;           // [E'] edge id -> position in the by-source order
+  size_t total;             // int32 words
+};
+
+constexpr int kScanChunk = 1024;
+
+inline int64_t scan_blocks(int64_t N) { return (N + kScanChunk - 1) / kScanChunk; }
+
+PrepScratch make_scratch(int64_t N, int64_t E) {
+  const size_t Ep = (size_t)(N + E);
+  PrepScratch s;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n * 4) / 4; return r; };
+  s.cnt_src = take(N);
+  s.cnt_tgt = take(N);
+  s.bsum = take(2 * (size_t)scan_blocks(N) + 2);
+  s.tmp_src = take(Ep);
+  s.tmp_tgt = take(Ep);
+  s.inv_src = take(Ep);
+  s.total = o;
+  return s;
+}
+
+__global__ void prep_edges_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
+                                  const int64_t* __restrict__ node_type, int64_t N, int64_t E, int T, int R,
+                                  int32_t* __restrict__ src_o, int32_t* __restrict__ tgt_o,
+                                  int32_t* __restrict__ combo_o, int32_t* __restrict__ cnt_src,
+                                  int32_t* __restrict__ cnt_tgt, int32_t* __restrict__ status) {
+  const int64_t Ep = E + N;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < Ep; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s, t, r;
+    int bad = 0;
+    if (e < E) {
+      s = edge_index[e];
+      t = edge_index[E + e];
+      r = edge_type[e];
+      if (s < 0 || s >= N || t < 0 || t >= N) { bad |= 1; s = min(max(s, (int64_t)0), N - 1); t = min(max(t, (int64_t)0), N - 1); }
+      if (r < 0 || r >= R) { bad |= 2; r = min(max(r, (int64_t)0), (int64_t)R - 1); }
+    } else {
+      s = t = e - E;  // self loop, own type index R (:420-421)
+      r = R;
+    }
+    int64_t ts = node_type[s], tt = node_type[t];
+    if (ts < 0 || ts >= T) { bad |= 4; ts = min(max(ts, (int64_t)0), (int64_t)T - 1); }
+    if (tt < 0 || tt >= T) { bad |= 4; tt = min(max(tt, (int64_t)0), (int64_t)T - 1); }
+    if (bad) atomicOr(status, bad);
+    src_o[e] = (int32_t)s;
+    tgt_o[e] = (int32_t)t;
+    combo_o[e] = (int32_t)((r * T + ts) * T + tt);
+    atomicAdd(cnt_src + s, 1);
+    atomicAdd(cnt_tgt + t, 1);
+  }
+}
+
+// ---- 3-phase exclusive scan of two length-N count arrays (blockIdx.y selects the array) ----
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* total) {
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int base = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[31];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_block_sums_kernel(const int32_t* __restrict__ cnt_a,
+                                                                       const int32_t* __restrict__ cnt_b, int64_t N,
+                                                                       int32_t* __restrict__ bsum, int nb) {
+  const int32_t* cnt = blockIdx.y ? cnt_b : cnt_a;
+  const int64_t i = (int64_t)blockIdx.x * kScanChunk + threadIdx.x;
+  int v = i < N ? cnt[i] : 0;
+  int total;
+  block_exclusive_scan_1024(v, &total);
+  if (threadIdx.x == 0) bsum[blockIdx.y * nb + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_sums_kernel(int32_t* __restrict__ bsum, int nb) {
+  int32_t* b = bsum + blockIdx.y * nb;
+  int carry = 0;
+  for (int base = 0; base < nb; base += kScanChunk) {
+    const int i = base + threadIdx.x;
+    int v = i < nb ? b[i] : 0;
+    int total;
+    int ex = block_exclusive_scan_1024(v, &total);
+    if (i < nb) b[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(kScanChunk) scan_apply_kernel(int32_t* __restrict__ cnt_a, int32_t* __restrict__ cnt_b,
+                                                                  int64_t N, const int32_t* __restrict__ bsum, int nb,
+                                                                  int32_t* __restrict__ rowptr_a,
+                                                                  int32_t* __restrict__ rowptr_b) {
+  int32_t* cnt = blockIdx.y ? cnt_b : cnt_a;
+  int32_t* rowptr = blockIdx.y ? rowptr_b : rowptr_a;
+  const int64_t i = (int64_t)blockIdx.x * kScanChunk + threadIdx.x;
+  int v = i < N ? cnt[i] : 0;
+  int total;
+  int ex = block_exclusive_scan_1024(v, &total) + bsum[blockIdx.y * nb + blockIdx.x];
+  if (i < N) {
+    rowptr[i] = ex;
+    cnt[i] = 0;  // becomes the fill cursor
+    if (i == N - 1) rowptr[N] = ex + v;
+  }
+}
+
+__global__ void prep_fill_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t Ep,
+                                 const int32_t* __restrict__ rowptr_src, const int32_t* __restrict__ rowptr_tgt,
+                                 int32_t* __restrict__ cur_src, int32_t* __restrict__ cur_tgt,
+                                 int32_t* __restrict__ tmp_src, int32_t* __restrict__ tmp_tgt) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < Ep; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = src[e], t = tgt[e];
+    tmp_src[rowptr_src[s] + atomicAdd(cur_src + s, 1)] = (int32_t)e;
+    tmp_tgt[rowptr_tgt[t] + atomicAdd(cur_tgt + t, 1)] = (int32_t)e;
+  }
+}
+
+// One warp per (node, order): restore ascending edge-id order inside the segment (== stable sort).
+__global__ void prep_sort_segments_kernel(int64_t N, const int32_t* __restrict__ rowptr_src,
+                                          const int32_t* __restrict__ rowptr_tgt, const int32_t* __restrict__ tmp_src,
+                                          const int32_t* __restrict__ tmp_tgt, int32_t* __restrict__ perm_src,
+                                          int32_t* __restrict__ perm_tgt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < 2 * N; w += nwarps) {
+    const bool by_tgt = w >= N;
+    const int64_t v = by_tgt ? w - N : w;
+    const int32_t* rowptr = by_tgt ? rowptr_tgt : rowptr_src;
+    const int32_t* tmp = by_tgt ? tmp_tgt : tmp_src;
+    int32_t* perm = by_tgt ? perm_tgt : perm_src;
+    const int beg = rowptr[v], deg = rowptr[v + 1] - beg;
+    if (deg <= 32) {
+      const int id = lane < deg ? tmp[beg + lane] : 0x7fffffff;
+      int rank = 0;
+      for (int j = 0; j < deg; ++j) rank += (__shfl_sync(0xffffffffu, id, j) < id);
+      if (lane < deg) perm[beg + rank] = id;
+    } else {
+      for (int i = lane; i < deg; i += 32) {
+        const int id = tmp[beg + i];
+        int rank = 0;
+        for (int j = 0; j < deg; ++j) rank += (tmp[beg + j] < id);
+        perm[beg + rank] = id;
+      }
+    }
+  }
+}
+
+__global__ void prep_payload_src_kernel(int64_t Ep, const int32_t* __restrict__ perm_src,
+                                        const int32_t* __restrict__ tgt, const int32_t* __restrict__ combo,
+                                        int32_t* __restrict__ csr_src_tgt, int32_t* __restrict__ csr_src_combo,
+                                        int32_t* __restrict__ inv_src) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x) {
+    const int e = perm_src[p];
+    csr_src_tgt[p] = tgt[e];
+    csr_src_combo[p] = combo[e];
+    inv_src[e] = (int32_t)p;
+  }
+}
+
+__global__ void prep_payload_tgt_kernel(int64_t Ep, const int32_t* __restrict__ perm_tgt,
+                                        const int32_t* __restrict__ src, const int32_t* __restrict__ combo,
+                                        const int32_t* __restrict__ inv_src, int32_t* __restrict__ csr_tgt_src,
+                                        int32_t* __restrict__ csr_tgt_combo, int32_t* __restrict__ csr_tgt_apos) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x) {
+    const int e = perm_tgt[p];
+    csr_tgt_src[p] = src[e];
+    csr_tgt_combo[p] = combo[e];
+    csr_tgt_apos[p] = inv_src[e];
+  }
+}
+
+inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  return (int)(g < cap ? g : cap);
+}
+
+}  // namespace
+
+}  // namespace qagnn
+
+using namespace qagnn;
+
+extern "C" int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layout* out) {
+  if (!out || N <= 0 || E < 0 || N + E >= (int64_t)1 << 31) return QAGNN_ERR_INVALID_ARGUMENT;
+  const size_t Ep = (size_t)(N + E);
+  size_t o = 0;
+  auto take = [&](size_t n_words) { size_t r = o; o += align_up(n_words * 4); return r; };
+  out->src = take(Ep);
+  out->tgt = take(Ep);
+  out->combo = take(Ep);
+  out->rowptr_src = take(N + 1);
+  out->rowptr_tgt = take(N + 1);
+  out->perm_src = take(Ep);
+  out->perm_tgt = take(Ep);
+  out->csr_src_tgt = take(Ep);
+  out->csr_src_combo = take(Ep);
+  out->csr_tgt_src = take(Ep);
+  out->csr_tgt_combo = take(Ep);
+  out->csr_tgt_apos = take(Ep);
+  out->status = take(4);
+  out->scratch = o;
+  o += make_scratch(N, E).total * 4;
+  out->total_bytes = align_up(o);
+  return QAGNN_OK;
+}
+
+extern "C" size_t qagnn_graph_prep_bytes(int64_t N, int64_t E) {
+  qagnn_prep_layout l;
+  if (qagnn_graph_prep_layout(N, E, &l) != QAGNN_OK) return 0;
+  return l.total_bytes;
+}
+
+extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* edge_type, const int64_t* node_type,
+                                    const qagnn_shape* shape, void* prep, size_t prep_bytes, int32_t validate,
+                                    void* stream) {
+  if (!shape || !node_type || !prep) return QAGNN_ERR_INVALID_ARGUMENT;
+  const int64_t N = shape->N, E = shape->E;
+  if (E > 0 && (!edge_index || !edge_type)) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (shape->T <= 0 || shape->R <= 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(N, E, &pl));
+  if (prep_bytes < pl.total_bytes) return QAGNN_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)prep;
+  auto I = [&](size_t off) { return (int32_t*)(base + off); };
+  const PrepScratch sc = make_scratch(N, E);
+  int32_t* scr = I(pl.scratch);
+  const int64_t Ep = N + E;
+  const int nb = (int)scan_blocks(N);
+
+  // zero the status word and the count arrays (status .. cnt_tgt are contiguous up to bsum)
+  QAGNN_CHECK_CUDA(cudaMemsetAsync(I(pl.status), 0, 16, st));
+  QAGNN_CHECK_CUDA(cudaMemsetAsync(scr + sc.cnt_src, 0, (sc.bsum - sc.cnt_src) * 4, st));
+
+  prep_edges_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(edge_index, edge_type, node_type, N, E, shape->T, shape->R,
+                                                       I(pl.src), I(pl.tgt), I(pl.combo), scr + sc.cnt_src,
+                                                       scr + sc.cnt_tgt, I(pl.status));
+  QAGNN_CHECK_LAUNCH();
+  scan_block_sums_kernel<<<dim3(nb, 2), kScanChunk, 0, st>>>(scr + sc.cnt_src, scr + sc.cnt_tgt, N, scr + sc.bsum, nb);
+  QAGNN_CHECK_LAUNCH();
+  scan_sums_kernel<<<dim3(1, 2), kScanChunk, 0, st>>>(scr + sc.bsum, nb);
+  QAGNN_CHECK_LAUNCH();
+  scan_apply_kernel<<<dim3(nb, 2), kScanChunk, 0, st>>>(scr + sc.cnt_src, scr + sc.cnt_tgt, N, scr + sc.bsum, nb,
+                                                         I(pl.rowptr_src), I(pl.rowptr_tgt));
+  QAGNN_CHECK_LAUNCH();
+  prep_fill_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(I(pl.src), I(pl.tgt), Ep, I(pl.rowptr_src), I(pl.rowptr_tgt),
+                                                      scr + sc.cnt_src, scr + sc.cnt_tgt, scr + sc.tmp_src,
+                                                      scr + sc.tmp_tgt);
+  QAGNN_CHECK_LAUNCH();
+  prep_sort_segments_kernel<<<grid_for(2 * N * 32, 256, 148 * 32), 256, 0, st>>>(
+      N, I(pl.rowptr_src), I(pl.rowptr_tgt), scr + sc.tmp_src, scr + sc.tmp_tgt, I(pl.perm_src), I(pl.perm_tgt));
+  QAGNN_CHECK_LAUNCH();
+  prep_payload_src_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_src), I(pl.tgt), I(pl.combo),
+                                                             I(pl.csr_src_tgt), I(pl.csr_src_combo),
+                                                             scr + sc.inv_src);
+  QAGNN_CHECK_LAUNCH();
+  prep_payload_tgt_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_tgt), I(pl.src), I(pl.combo),
+                                                             scr + sc.inv_src, I(pl.csr_tgt_src),
+                                                             I(pl.csr_tgt_combo), I(pl.csr_tgt_apos));
+  QAGNN_CHECK_LAUNCH();
+  if (validate) {
+    int32_t h = 0;
+    QAGNN_CHECK_CUDA(cudaMemcpyAsync(&h, I(pl.status), 4, cudaMemcpyDeviceToHost, st));
+    QAGNN_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (h != 0) return QAGNN_ERR_INDEX_RANGE;
+  }
+  return QAGNN_OK;
+}

@@ -1,0 +1,124 @@
+"""Small host-side layers around the hot path (the caller side of SURVEY.md §8b), kept as plain
+PyTorch.  Constructor arguments and state_dict key names follow the reference's utils/layers.py
+so checkpoints load unchanged:
+    GELU                    utils/layers.py:10-22   (tanh approximation)
+    MLP                     utils/layers.py:47-87   ('layers.{i}-Linear', '{i}-LayerNorm', ...)
+    MultiheadAttPoolLayer   utils/layers.py:324-371 (+ MatrixVectorScaledDotProductAttention :276-299)
+    CustomizedEmbedding     utils/layers.py:571-607
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def gelu(x):
+    """tanh-approximation GELU, the form the reference uses everywhere (utils/layers.py:10-14)."""
+    return F.gelu(x, approximate="tanh")
+
+
+class GELU(nn.Module):
+    def forward(self, x):
+        return gelu(x)
+
+
+class MLP(nn.Module):
+    """num_layers hidden blocks (Linear, Dropout, [BatchNorm1d | LayerNorm], activation) + output Linear."""
+    _ACT = {"gelu": GELU, "relu": nn.ReLU, "tanh": nn.Tanh}
+
+    def __init__(self, input_size, hidden_size, output_size, num_layers, dropout, batch_norm=False,
+                 init_last_layer_bias_to_zero=False, layer_norm=False, activation="gelu"):
+        super().__init__()
+        if batch_norm and layer_norm:
+            raise ValueError("batch_norm and layer_norm are mutually exclusive")
+        self.input_size, self.hidden_size, self.output_size = input_size, hidden_size, output_size
+        self.num_layers, self.dropout, self.batch_norm, self.layer_norm = num_layers, dropout, batch_norm, layer_norm
+        blocks = nn.Sequential()
+        width = input_size
+        for i in range(num_layers):
+            blocks.add_module(f"{i}-Linear", nn.Linear(width, hidden_size))
+            blocks.add_module(f"{i}-Dropout", nn.Dropout(dropout))
+            if batch_norm:
+                blocks.add_module(f"{i}-BatchNorm1d", nn.BatchNorm1d(hidden_size))
+            if layer_norm:
+                blocks.add_module(f"{i}-LayerNorm", nn.LayerNorm(hidden_size))
+            blocks.add_module(f"{i}-{activation}", self._ACT[activation.lower()]())
+            width = hidden_size
+        blocks.add_module(f"{num_layers}-Linear", nn.Linear(width, output_size))
+        self.layers = blocks
+        if init_last_layer_bias_to_zero:
+            self.layers[-1].bias.data.zero_()
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class MultiheadAttPoolLayer(nn.Module):
+    """Pools k [b, l, d_k_original] with a query q [b, d_q_original]: n_head scaled dot-product
+    attentions over the l positions, masked positions excluded.  Returns (pooled [b, n_head*d_v],
+    attn [n_head*b, l]) with the reference's head-major attn layout."""
+
+    def __init__(self, n_head, d_q_original, d_k_original, dropout=0.1):
+        super().__init__()
+        if d_k_original % n_head != 0:
+            raise ValueError("d_k_original must be divisible by n_head")
+        self.n_head = n_head
+        self.d_k = self.d_v = d_k_original // n_head
+        self.w_qs = nn.Linear(d_q_original, n_head * self.d_k)
+        self.w_ks = nn.Linear(d_k_original, n_head * self.d_k)
+        self.w_vs = nn.Linear(d_k_original, n_head * self.d_v)
+        nn.init.normal_(self.w_qs.weight, mean=0, std=math.sqrt(2.0 / (d_q_original + self.d_k)))
+        nn.init.normal_(self.w_ks.weight, mean=0, std=math.sqrt(2.0 / (d_k_original + self.d_k)))
+        nn.init.normal_(self.w_vs.weight, mean=0, std=math.sqrt(2.0 / (d_k_original + self.d_v)))
+        self.temperature = math.sqrt(self.d_k)
+        self.attn_dropout = nn.Dropout(0.1)  # MatrixVectorScaledDotProductAttention's own dropout
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, q, k, mask=None):
+        b, l, _ = k.shape
+        nh, dk, dv = self.n_head, self.d_k, self.d_v
+        qs = self.w_qs(q).view(b, nh, dk)
+        ks = self.w_ks(k).view(b, l, nh, dk)
+        vs = self.w_vs(k).view(b, l, nh, dv)
+        logits = torch.einsum("bhd,blhd->hbl", qs, ks) / self.temperature
+        if mask is not None:
+            logits = logits.masked_fill(mask.unsqueeze(0), float("-inf"))
+        attn = self.attn_dropout(torch.softmax(logits, dim=2))
+        pooled = torch.einsum("hbl,blhd->bhd", attn, vs).reshape(b, nh * dv)
+        return self.dropout(pooled), attn.reshape(nh * b, l)
+
+
+class CustomizedEmbedding(nn.Module):
+    """Concept embedding table with an optional Linear+GELU projection when the table width differs
+    from the GNN width."""
+
+    def __init__(self, concept_num, concept_in_dim, concept_out_dim, use_contextualized=False,
+                 pretrained_concept_emb=None, freeze_ent_emb=True, scale=1.0, init_range=0.02):
+        super().__init__()
+        self.scale = scale
+        self.use_contextualized = use_contextualized
+        if not use_contextualized:
+            self.emb = nn.Embedding(concept_num, concept_in_dim)
+            if pretrained_concept_emb is not None:
+                self.emb.weight.data.copy_(pretrained_concept_emb)
+            else:
+                self.emb.weight.data.normal_(mean=0.0, std=init_range)
+            if freeze_ent_emb:
+                for p in self.emb.parameters():
+                    p.requires_grad = False
+        if concept_in_dim != concept_out_dim:
+            self.cpt_transform = nn.Linear(concept_in_dim, concept_out_dim)
+            self.activation = GELU()
+
+    def _project(self, e):
+        e = e * self.scale
+        return self.activation(self.cpt_transform(e)) if hasattr(self, "cpt_transform") else e
+
+    def forward(self, index, contextualized_emb=None):
+        if contextualized_emb is not None:
+            if index.size(0) != contextualized_emb.size(0):
+                raise ValueError("batch size mismatch between index and contextualized_emb")
+            table = self._project(contextualized_emb)
+            return table.gather(1, index.unsqueeze(-1).expand(-1, -1, table.size(-1)))
+        return self._project(self.emb(index))

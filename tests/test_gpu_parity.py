@@ -1,0 +1,176 @@
+"""Parity of the CUDA path (through the C ABI) against the goldens minted from the reference and
+against the CPU oracle.  Needs a GPU: run with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import qagnn_b200
+from oracle import make_goldens as MG
+from oracle import qagnn_oracle as O
+from qagnn_b200.modeling_qagnn import GraphPrep
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mp_module(c, fx, sd):
+    mod = qagnn_b200.QAGNN_Message_Passing(None, c["k"], fx["n_ntype"], fx["n_etype"], c["D"], c["D"], c["D"]).eval()
+    mod.load_state_dict(sd, strict=True)
+    return mod.to(DEV)
+
+
+def _dev(inp):
+    return {k: v.to(DEV) for k, v in inp.items()}
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("mp"))
+def test_graph_prep_bit_exact(name):
+    fx = Hh.load_golden(name)
+    inp, _ = Hh.regen_mp_inputs(fx)
+    d = _dev(inp)
+    prep = GraphPrep(d["edge_index"], d["edge_type"], d["node_type"], fx["n_ntype"], fx["n_etype"], fx["case"]["n"])
+    ref = O.graph_prep_oracle(inp["edge_index"], inp["edge_type"], inp["node_type"], fx["n_ntype"], fx["n_etype"])
+    got = {k: prep.array(k).cpu().numpy().astype(np.int64) for k in
+           ("src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt", "csr_src_tgt", "csr_src_combo",
+            "csr_tgt_src", "csr_tgt_combo", "csr_tgt_apos")}
+    for key in ("src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt"):
+        assert np.array_equal(got[key], ref[key]), key
+    assert np.array_equal(got["csr_src_tgt"], ref["tgt"][ref["perm_src"]])
+    assert np.array_equal(got["csr_src_combo"], ref["combo"][ref["perm_src"]])
+    assert np.array_equal(got["csr_tgt_src"], ref["src"][ref["perm_tgt"]])
+    assert np.array_equal(got["csr_tgt_combo"], ref["combo"][ref["perm_tgt"]])
+    inv = np.empty_like(ref["perm_src"]); inv[ref["perm_src"]] = np.arange(len(inv))
+    assert np.array_equal(got["csr_tgt_apos"], inv[ref["perm_tgt"]])
+    assert torch.equal(prep.edge_index_prime().cpu(), fx["edge_index_prime"])
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("mp"))
+def test_message_passing_matches_reference_golden(name):
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sd = Hh.regen_mp_inputs(fx)
+    d = _dev(inp)
+    mod = _mp_module(c, fx, sd)
+    extra = mod.node_feature_extra(d["node_type"], d["node_score"])
+    Hh.assert_close(extra, fx["extra"], "node_feature_extra")
+    out, layers = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"], return_layers=True)
+    for l, ref_l in fx["layers"].items():
+        Hh.assert_close(layers[l], ref_l["x"], f"x[{l}]")
+    Hh.assert_close(out, fx["out"], "out")
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("mp"))
+def test_layerwise_api_matches_fused_forward(name):
+    """mp_helper-style use (one GATConvE.forward per layer + GELU) equals the fused qagnn_mp_forward."""
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sd = Hh.regen_mp_inputs(fx)
+    d = _dev(inp)
+    mod = _mp_module(c, fx, sd)
+    extra = mod.node_feature_extra(d["node_type"], d["node_score"])
+    X = d["H"].view(-1, c["D"]).contiguous()
+    nt = d["node_type"].view(-1)
+    for l in range(c["k"]):
+        X, (ei2, alpha) = mod.gnn_layers[l](X, d["edge_index"], d["edge_type"], nt, extra, return_attention_weights=True)
+        X = mod.activation(X)
+        if l in fx["layers"]:
+            Hh.assert_close(alpha, fx["layers"][l]["alpha"], f"alpha[{l}]")
+            Hh.assert_close(X, fx["layers"][l]["x"], f"x[{l}]")
+            assert torch.equal(ei2.cpu(), fx["edge_index_prime"])
+    _, layers = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"], return_layers=True)
+    Hh.assert_close(X, layers[-1].cpu(), "layerwise vs fused", atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("layer"))
+def test_gatconve_matches_reference_golden(name):
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    x, extra, node_type, ei, et, sd = Hh.regen_layer_inputs(fx)
+    D = c["D"]
+    enc = torch.nn.Sequential(torch.nn.Linear(fx["n_etype"] + 1 + fx["n_ntype"] * 2, D), torch.nn.BatchNorm1d(D),
+                              torch.nn.ReLU(), torch.nn.Linear(D, D))
+    layer = qagnn_b200.GATConvE(None, D, fx["n_ntype"], fx["n_etype"], enc, head_count=c["H"]).eval()
+    layer.load_state_dict({k[len("gnn_layers.0."):]: v for k, v in sd.items() if k.startswith("gnn_layers.0.")}, strict=True)
+    layer = layer.to(DEV)
+    out, (ei2, alpha) = layer(x.to(DEV), ei.to(DEV), et.to(DEV), node_type.to(DEV), extra.to(DEV),
+                              return_attention_weights=True)
+    assert torch.equal(ei2.cpu(), fx["edge_index_prime"])
+    Hh.assert_close(alpha, fx["alpha"], "alpha")
+    Hh.assert_close(out, fx["out"], "out")
+    # softmax groups by SOURCE: alpha sums to one over the out-edges of every source node
+    sums = torch.zeros(x.size(0), c["H"], device=DEV).index_add_(0, ei2[0].to(DEV), alpha)
+    assert torch.allclose(sums, torch.ones_like(sums), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("decoder"))
+def test_decoder_matches_reference_golden(name):
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sent_vecs, concept_ids = MG.build_decoder_inputs(c, fx["n_etype"])
+    dec = qagnn_b200.QAGNN(None, c["k"], fx["n_ntype"], fx["n_etype"], c["sent_dim"], c["n_concept"], c["D"],
+                           c["concept_in_dim"], c["n_head"], c["D"], c["n_fc_layer"], 0.2, 0.2, 0.2).eval()
+    dec.load_state_dict(fx["state_dict"], strict=True)
+    dec = dec.to(DEV)
+    d = _dev(inp)
+    logits, pool_attn = dec(sent_vecs.to(DEV), concept_ids.to(DEV), d["node_type"], d["node_score"], d["adj_lengths"],
+                            (d["edge_index"], d["edge_type"]))
+    Hh.assert_close(pool_attn, fx["pool_attn"], "pool_attn")
+    Hh.assert_close(logits, fx["logits"], "logits")
+
+
+def test_out_of_range_indices_raise():
+    inp = O.synth_graph_batch(2, 10, 20, 64, 38, 0)
+    sd = O.random_state_dict(1, 64)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, 1, 4, 38, 64, 64, 64).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    d = _dev(inp)
+    bad = d["edge_index"].clone(); bad[0, 3] = 20  # == N
+    with pytest.raises(IndexError):
+        mod(d["H"], (bad, d["edge_type"]), d["node_type"], d["node_score"])
+    bad_t = d["edge_type"].clone(); bad_t[0] = 38
+    with pytest.raises(IndexError):
+        mod(d["H"], (d["edge_index"], bad_t), d["node_type"], d["node_score"])
+    with pytest.raises(NotImplementedError):
+        mod.train()(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+
+
+# ---- full-size (BASELINE.json configs[1]) properties -----------------------------------------
+@pytest.fixture(scope="module")
+def cfg2():
+    B, n, e, D, k = 320, 200, 1000, 200, 5
+    inp = O.synth_graph_batch(B, n, e, D, 38, seed=0, realistic=True)
+    sd = O.random_state_dict(k, D, 4, 38, "peaky", seed=0)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D).eval()
+    mod.load_state_dict(sd)
+    return inp, sd, mod.to(DEV)
+
+
+def test_cfg2_deterministic_and_oracle_on_a_slice(cfg2):
+    inp, sd, mod = cfg2
+    d = _dev(inp)
+    a = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    b = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    assert torch.equal(a, b), "two runs on the same inputs must be bit-identical (no atomics in the data path)"
+    # graphs are independent: the first 12 graphs evaluated alone by the CPU oracle
+    g, n = 12, 200
+    sel = inp["edge_index"][0] < g * n
+    ref = O.message_passing_forward(sd, inp["H"][:g], inp["edge_index"][:, sel], inp["edge_type"][sel],
+                                    inp["node_type"][:g], inp["node_score"][:g], 5, 4, 38)
+    Hh.assert_close(a[:g], ref, "cfg2 slice vs oracle")
+
+
+def test_cfg2_batch_independence_and_edge_permutation(cfg2):
+    inp, sd, mod = cfg2
+    d = _dev(inp)
+    full = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    # (1) a sub-batch gives the same rows as the full batch
+    g, n = 40, 200
+    sel = d["edge_index"][0] < g * n
+    sub = mod(d["H"][:g], (d["edge_index"][:, sel], d["edge_type"][sel]), d["node_type"][:g], d["node_score"][:g])
+    Hh.assert_close(sub, full[:g].cpu(), "sub-batch vs full batch", atol=1e-6, rtol=1e-6)
+    # (2) the order of the edge list is irrelevant up to summation order
+    perm = torch.randperm(d["edge_index"].size(1), device=DEV, generator=torch.Generator(DEV).manual_seed(0))
+    shuf = mod(d["H"], (d["edge_index"][:, perm], d["edge_type"][perm]), d["node_type"], d["node_score"])
+    Hh.assert_close(shuf, full.cpu(), "edge permutation", atol=2e-5, rtol=1e-4)

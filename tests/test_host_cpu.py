@@ -1,0 +1,85 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares (no
+compute calls without a GPU), layout queries, module/state_dict contract, batch packing."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import qagnn_b200
+from oracle import qagnn_oracle as O
+from qagnn_b200 import _lib
+from qagnn_b200.data import pack_adj
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        from qagnn_b200 import build
+        build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "qagnn_b200.h")).read()
+    declared = set(re.findall(r"\b(qagnn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/qagnn_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
+    assert lib.qagnn_abi_version() == 1
+    assert lib.qagnn_status_string(-3).decode().startswith("index out of range")
+
+
+def test_size_queries_and_argument_checks(lib):
+    pl = _lib.PrepLayout()
+    assert lib.qagnn_graph_prep_layout(64000, 320000, C.byref(pl)) == 0
+    assert pl.total_bytes == lib.qagnn_graph_prep_bytes(64000, 320000) > 12 * 4 * 384000
+    offs = [getattr(pl, f) for f, _ in _lib.PrepLayout._fields_[1:]]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert lib.qagnn_graph_prep_layout(0, 10, C.byref(pl)) == -1
+    s = _lib.Shape(64000, 320000, 200, 4, 4, 38, 5, 200)
+    assert lib.qagnn_fold_bytes(C.byref(s)) > 5 * (3 * 200 * 400 + 2 * 624 * 200) * 4
+    assert lib.qagnn_forward_workspace_bytes(C.byref(s)) >= 64000 * 200 * 4 * 8
+    bad = _lib.Shape(64000, 320000, 200, 3, 4, 38, 5, 200)  # D % H != 0
+    assert lib.qagnn_fold_bytes(C.byref(bad)) == 0
+    # null pointers are rejected before any CUDA call
+    assert lib.qagnn_graph_prep(None, None, None, C.byref(s), None, 0, 0, None) == -1
+    assert lib.qagnn_mp_forward(C.byref(s), None, None, None, None, None, None, None, None, 0, None) == -1
+
+
+def test_state_dict_contract_and_cpu_refusal():
+    mod = qagnn_b200.QAGNN_Message_Passing(None, 5, 4, 38, 200, 200, 200).eval()
+    sd = O.random_state_dict(5, 200)
+    assert sorted(mod.state_dict().keys()) == sorted(sd.keys())
+    assert sum(p.numel() for p in mod.parameters()) == 2148200
+    mod.load_state_dict(sd, strict=True)
+    assert mod.gnn_layers[3].edge_encoder is mod.edge_encoder  # one shared module, k aliases
+    inp = O.synth_graph_batch(2, 10, 20, 200, 38, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod(inp["H"], (inp["edge_index"], inp["edge_type"]), inp["node_type"], inp["node_score"])
+
+
+def test_decoder_state_dict_keys_match_reference_golden():
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "decoder_fc1.pt"), weights_only=False)
+    c = fx["case"]
+    dec = qagnn_b200.QAGNN(None, c["k"], 4, 38, c["sent_dim"], c["n_concept"], c["D"], c["concept_in_dim"], c["n_head"],
+                           c["D"], c["n_fc_layer"], 0.2, 0.2, 0.2)
+    assert sorted(dec.state_dict().keys()) == sorted(fx["state_dict"].keys())
+    dec.load_state_dict(fx["state_dict"], strict=True)
+
+
+def test_pack_adj_equals_batch_graph():
+    g = torch.Generator().manual_seed(0)
+    bs, nc, n = 3, 5, 50
+    ei = [[torch.randint(0, n, (2, int(torch.randint(0, 40, (1,), generator=g))), generator=g) for _ in range(nc)] for _ in range(bs)]
+    et = [[torch.randint(0, 38, (e.size(1),), generator=g) for e in row] for row in ei]
+    packed = pack_adj(ei, et, n, pin=False)
+    ref_ei, ref_et = O.batch_graph(sum(ei, []), sum(et, []), n)
+    assert torch.equal(packed.edge_index, ref_ei) and torch.equal(packed.edge_type, ref_et)
+    assert packed.graph_ptr[-1] == ref_ei.size(1)
+    lm = qagnn_b200.LM_QAGNN.batch_graph(None, sum(ei, []), sum(et, []), n)
+    assert torch.equal(lm[0], ref_ei) and torch.equal(lm[1], ref_et)
