@@ -164,6 +164,21 @@ int32_t qagnn_mp_forward(const qagnn_shape *shape, const float *H_in, const int6
 /* Launch counters since load (kernels this library enqueued); for bench.py's gpu_launches. */
 int64_t qagnn_launch_count(void);
 
+/* Optional device-side stage timing (diagnostics for bench.py's roofline; single-threaded use).
+ * While enabled, every forward brackets its stages with cudaEvents on the launching stream.
+ * qagnn_profile_read synchronises those events and returns, per stage, the summed milliseconds and
+ * the number of timed intervals since the last enable.  Stages: */
+enum {
+  QAGNN_PROF_GRAPH_PREP = 0,   /* qagnn_graph_prep                                   */
+  QAGNN_PROF_PROJECTION = 1,   /* [x|extra] @ Wp^T  (Q|Kx|Mx)                         */
+  QAGNN_PROF_MESSAGE_PASSING = 2, /* logits + per-source softmax + rescale + per-target sum */
+  QAGNN_PROF_NODE_MLP = 3,     /* mlp.0 + BN + ReLU + mlp.3 (+GELU)                    */
+  QAGNN_PROF_PRO_EPILOGUE = 4, /* node_feature_extra and Vh/Vx                         */
+  QAGNN_PROF_STAGES = 5
+};
+int32_t qagnn_profile_enable(int32_t on);
+int32_t qagnn_profile_read(double *ms_out /* [QAGNN_PROF_STAGES] */, int64_t *count_out /* [QAGNN_PROF_STAGES] */);
+
 #ifdef __cplusplus
 }
 #endif

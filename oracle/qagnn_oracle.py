@@ -279,8 +279,9 @@ def synth_graph_batch(B, n, e_per_graph, D, n_etype=38, seed=0, realistic=False)
 
     Plain variant: edge endpoints ~ U{0..n-1}^2 (+g*n), duplicates and i->i allowed; edge_type
     ~ U{0..R-1}; node_type ~ U{0,1,2} with node 0 of each graph = 3; H ~ N(0,1)*0.5; scores N(0,1).
-    Realistic variant: adj_lengths ~ U{8..n}, edges only among valid nodes, forward half + exact
-    inverse half with type + R/2, context node 0 linked to q/a nodes with types 0/1.
+    Realistic variant: adj_lengths ~ U{8..n}, min(e/2, 2.5*len) forward edges among the valid nodes +
+    the exact inverse half with type + R/2, context node 0 linked to the q/a nodes with types 0/1,
+    padded nodes isolated (self loop only).
     """
     g = torch.Generator().manual_seed(seed)
     H = torch.randn(B, n, D, generator=g) * 0.5
@@ -305,7 +306,7 @@ def synth_graph_batch(B, n, e_per_graph, D, n_etype=38, seed=0, realistic=False)
             node_type[b, 1:] = 2
             node_type[b, 1:1 + nq] = 0
             node_type[b, 1 + nq:1 + nq + na] = 1
-            ef = e_per_graph // 2
+            ef = min(e_per_graph // 2, int(2.5 * L))  # ~2.5 forward edges per node (SURVEY.md §8d cfg 3)
             nctx = min(nq + na, ef)
             s = torch.randint(1, max(L, 2), (ef,), generator=g).clamp_(max=L - 1)
             t = torch.randint(1, max(L, 2), (ef,), generator=g).clamp_(max=L - 1)

@@ -59,6 +59,8 @@ EXPORTS = {
     "qagnn_node_feature_extra": (C.c_int32, [C.POINTER(Shape), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "qagnn_mp_forward": (C.c_int32, [C.POINTER(Shape), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "qagnn_launch_count": (C.c_int64, []),
+    "qagnn_profile_enable": (C.c_int32, [C.c_int32]),
+    "qagnn_profile_read": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -81,6 +83,18 @@ def load():
         raise RuntimeError("libqagnn_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+PROF_STAGES = ("graph_prep", "projection", "message_passing", "node_mlp", "pro_epilogue")
+
+
+def profile_read():
+    """{stage: (ms, intervals)} since the last qagnn_profile_enable(1)."""
+    lib = load()
+    ms = (C.c_double * len(PROF_STAGES))()
+    cnt = (C.c_int64 * len(PROF_STAGES))()
+    check(lib.qagnn_profile_read(ms, cnt), "qagnn_profile_read")
+    return {n: (ms[i], cnt[i]) for i, n in enumerate(PROF_STAGES)}
 
 
 class QagnnError(RuntimeError):

@@ -17,6 +17,38 @@ int32_t cuda_fail(cudaError_t e) {
   return QAGNN_ERR_CUDA;
 }
 
+// ---- stage timing -----------------------------------------------------------------------------------
+namespace {
+constexpr int kProfMax = 8192;
+struct ProfState {
+  bool on = false;
+  int n = 0;                       // recorded intervals
+  cudaEvent_t ev[kProfMax][2];
+  int created = 0;
+  int stage[kProfMax];
+  int open_idx[QAGNN_PROF_STAGES];
+} g_prof;
+}  // namespace
+
+void prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n >= kProfMax) { if (g_prof.on) g_prof.open_idx[stage] = -1; return; }
+  const int i = g_prof.n++;
+  if (i >= g_prof.created) {
+    cudaEventCreate(&g_prof.ev[i][0]);
+    cudaEventCreate(&g_prof.ev[i][1]);
+    g_prof.created = i + 1;
+  }
+  g_prof.stage[i] = stage;
+  g_prof.open_idx[stage] = i;
+  cudaEventRecord(g_prof.ev[i][0], st);
+}
+
+void prof_end(int stage, cudaStream_t st) {
+  if (!g_prof.on) return;
+  const int i = g_prof.open_idx[stage];
+  if (i >= 0) cudaEventRecord(g_prof.ev[i][1], st);
+}
+
 WorkLayout make_work_layout(const qagnn_shape& s) {
   WorkLayout W;
   const size_t N = (size_t)s.N, D = (size_t)s.D, Ep = (size_t)(s.N + s.E), H = (size_t)s.H;
@@ -71,19 +103,26 @@ int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
   const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
   float* qkm = ws + W.qkm;
   float* aggr = aggr_out ? aggr_out : ws + W.aggr;
-  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                        (:440, :464-466 node part, :469)
-  QAGNN_RETURN_IF(sgemm_tn(x, D, D, extra, D, D, lb + L.wp, 2 * D, lb + L.bp, qkm, 3 * D, s.N, 3 * D, ACT_NONE, st));
-  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
-  QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
-                                         ws + W.alpha, aggr, alpha_out, st));
-  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
-  QAGNN_RETURN_IF(sgemm_tn(aggr, D, D, nullptr, 0, 0, lb + L.w1, D, lb + L.b1, ws + W.hmid, D, s.N, D, ACT_RELU, st));
-  QAGNN_RETURN_IF(sgemm_tn(ws + W.hmid, D, D, nullptr, 0, 0, lb + L.w2, D, lb + L.b2, out, D, s.N, D, final_act, st));
+  {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
+    ProfScope ps(QAGNN_PROF_PROJECTION, st);
+    QAGNN_RETURN_IF(sgemm_tn(x, D, D, extra, D, D, lb + L.wp, 2 * D, lb + L.bp, qkm, 3 * D, s.N, 3 * D, ACT_NONE, st));
+  }
+  {  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
+    ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
+    QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
+                                           ws + W.alpha, aggr, alpha_out, st));
+  }
+  {  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
+    ProfScope ps(QAGNN_PROF_NODE_MLP, st);
+    QAGNN_RETURN_IF(sgemm_tn(aggr, D, D, nullptr, 0, 0, lb + L.w1, D, lb + L.b1, ws + W.hmid, D, s.N, D, ACT_RELU, st));
+    QAGNN_RETURN_IF(sgemm_tn(ws + W.hmid, D, D, nullptr, 0, 0, lb + L.w2, D, lb + L.b2, out, D, s.N, D, final_act, st));
+  }
   return QAGNN_OK;
 }
 
 int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, const int64_t* node_type,
                       const float* node_score, const float* folded, float* extra, float* ws, cudaStream_t st) {
+  ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   const int D = s.D, Dh = D / 2;
   const int64_t n = s.N * Dh;
   int64_t g = (n + 255) / 256;
@@ -118,6 +157,26 @@ extern "C" const char* qagnn_status_string(int32_t status) {
 extern "C" const char* qagnn_last_cuda_error(void) { return g_cuda_err; }
 
 extern "C" int64_t qagnn_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int32_t qagnn_profile_enable(int32_t on) {
+  g_prof.on = on != 0;
+  g_prof.n = 0;
+  for (int i = 0; i < QAGNN_PROF_STAGES; ++i) g_prof.open_idx[i] = -1;
+  return QAGNN_OK;
+}
+
+extern "C" int32_t qagnn_profile_read(double* ms_out, int64_t* count_out) {
+  if (!ms_out || !count_out) return QAGNN_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < QAGNN_PROF_STAGES; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    QAGNN_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[i][1]));
+    float ms = 0.f;
+    QAGNN_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]));
+    ms_out[g_prof.stage[i]] += ms;
+    count_out[g_prof.stage[i]] += 1;
+  }
+  return QAGNN_OK;
+}
 
 extern "C" size_t qagnn_forward_workspace_bytes(const qagnn_shape* shape) {
   if (check_shape_fwd(shape) != QAGNN_OK) return 0;
@@ -175,5 +234,6 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
     x = xo;
   }
   // output = GELU(Vh(H) + Vx(X))                                             (:92)
+  ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   return sgemm_tn(H_in, s.D, s.D, x, s.D, s.D, f + L.vcat, 2 * s.D, f + L.vbias, out, s.D, s.N, s.D, ACT_GELU, st);
 }

@@ -35,6 +35,15 @@ int32_t cuda_fail(cudaError_t e);  // records the error text, returns QAGNN_ERR_
     if (s__ != QAGNN_OK) return s__; \
   } while (0)
 
+// ---- optional stage timing (qagnn_profile_*) -------------------------------------------------------
+void prof_begin(int stage, cudaStream_t st);
+void prof_end(int stage, cudaStream_t st);
+struct ProfScope {
+  int stage; cudaStream_t st;
+  ProfScope(int s, cudaStream_t t) : stage(s), st(t) { prof_begin(stage, st); }
+  ~ProfScope() { prof_end(stage, st); }
+};
+
 // ---- folded-weight blob ---------------------------------------------------------------------------
 // All offsets in floats from the start of the blob.  C = (R+1)*T*T rows in the edge tables.
 struct FoldLayout {

@@ -268,6 +268,7 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   const int64_t Ep = N + E;
   const int nb = (int)scan_blocks(N);
 
+  ProfScope ps(QAGNN_PROF_GRAPH_PREP, st);
   // zero the status word and the count arrays (status .. cnt_tgt are contiguous up to bsum)
   QAGNN_CHECK_CUDA(cudaMemsetAsync(I(pl.status), 0, 16, st));
   QAGNN_CHECK_CUDA(cudaMemsetAsync(scr + sc.cnt_src, 0, (sc.bsum - sc.cnt_src) * 4, st));
