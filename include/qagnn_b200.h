@@ -113,6 +113,8 @@ typedef struct qagnn_prep_layout {
   size_t csr_tgt_src;  /* [E'] src[perm_tgt[p]]                                       */
   size_t csr_tgt_combo;/* [E'] combo[perm_tgt[p]]                                     */
   size_t csr_tgt_apos; /* [E'] position of edge perm_tgt[p] in the by-source order      */
+  size_t pk_src;       /* [E'] (tgt - graph_base) << 16 | combo, by-source order (n_per_graph > 0 only) */
+  size_t pk_tgt;       /* [E'] (src - graph_base) << 16 | combo, by-target order (n_per_graph > 0 only) */
   size_t status;       /* [4]  device-side error word + counters                        */
   size_t scratch;      /* internal                                                     */
 } qagnn_prep_layout;
@@ -122,7 +124,10 @@ size_t qagnn_graph_prep_bytes(int64_t N, int64_t E);
 
 /* edge_index int64 [2,E] (row 0 = source, row 1 = target), edge_type int64 [E] in [0,R),
  * node_type int64 [N] in [0,T).  validate != 0: synchronise `stream` and return
- * QAGNN_ERR_INDEX_RANGE if any index is out of range (the kernels clamp, never fault). */
+ * QAGNN_ERR_INDEX_RANGE if any index is out of range (the kernels clamp, never fault).
+ * shape->n_per_graph > 0 additionally asserts that no edge crosses a sub-graph boundary
+ * (src / n_per_graph == tgt / n_per_graph), which LM_QAGNN.batch_graph guarantees; a violation is
+ * reported as QAGNN_ERR_INDEX_RANGE as well.  It enables the shared-memory-tiled kernels. */
 int32_t qagnn_graph_prep(const int64_t *edge_index, const int64_t *edge_type, const int64_t *node_type,
                          const qagnn_shape *shape, void *prep, size_t prep_bytes, int32_t validate,
                          void *stream);

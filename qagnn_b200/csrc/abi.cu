@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/qagnn_b200.h: the forward orchestration of
 // GATConvE (modeling/modeling_qagnn.py:411-484) and QAGNN_Message_Passing (modeling_qagnn.py:53-95).
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -54,7 +55,8 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   const size_t N = (size_t)s.N, D = (size_t)s.D, Ep = (size_t)(s.N + s.E), H = (size_t)s.H;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n * 4) / 4; return r; };
-  W.qkm = take(N * 3 * D);
+  const size_t DP = (size_t)head_dim_padded((int)(D / H));
+  W.qkm = take(N * 3 * (D > H * DP ? D : H * DP));
   W.aggr = take(N * D);
   W.hmid = take(N * D);
   W.xa = take(N * D);
@@ -95,22 +97,40 @@ int32_t check_shape_fwd(const qagnn_shape* s) {
   return QAGNN_OK;
 }
 
+// Path selection: the shared-memory-tiled kernel when the batch is made of equal small sub-graphs
+// (shape.n_per_graph > 0 and the tiles fit), else the general CSR kernels.  QAGNN_MP_PATH=csr forces
+// the general path (A/B measurements).
+bool use_headtile(const qagnn_shape& s) {
+  static const int forced = [] {
+    const char* e = getenv("QAGNN_MP_PATH");
+    return (e && strcmp(e, "csr") == 0) ? 1 : 0;
+  }();
+  return !forced && headtile_supported(s);
+}
+
 // one GATConvE layer; `final_act` = ACT_NONE for the bare layer, ACT_GELU when called from mp_helper
 int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, int layer, const float* x,
                       const float* extra, const void* prep, const qagnn_prep_layout& pl, const float* folded,
-                      float* out, float* alpha_out, float* aggr_out, float* ws, Act final_act, cudaStream_t st) {
+                      float* out, float* alpha_out, float* aggr_out, float* ws, Act final_act, bool tiled,
+                      cudaStream_t st) {
   const int D = s.D;
   const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
   float* qkm = ws + W.qkm;
   float* aggr = aggr_out ? aggr_out : ws + W.aggr;
   {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
     ProfScope ps(QAGNN_PROF_PROJECTION, st);
-    QAGNN_RETURN_IF(sgemm_tn(x, D, D, extra, D, D, lb + L.wp, 2 * D, lb + L.bp, qkm, 3 * D, s.N, 3 * D, ACT_NONE, st));
+    HeadMajorOut hm{tiled ? 1 : 0, D, D / s.H, head_dim_padded(D / s.H), s.H};
+    QAGNN_RETURN_IF(sgemm_tn(x, D, D, extra, D, D, lb + L.wp, 2 * D, lb + L.bp, qkm, 3 * D, s.N, 3 * D, ACT_NONE, st, hm));
   }
   {  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
-    QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
-                                           ws + W.alpha, aggr, alpha_out, st));
+    if (tiled) {
+      QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
+                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, st));
+    } else {
+      QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
+                                             ws + W.alpha, aggr, alpha_out, st));
+    }
   }
   {  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
     ProfScope ps(QAGNN_PROF_NODE_MLP, st);
@@ -194,8 +214,10 @@ extern "C" int32_t qagnn_gatconve_forward(const qagnn_shape* shape, int32_t laye
   if (workspace_bytes < W.total * sizeof(float)) return QAGNN_ERR_WORKSPACE;
   qagnn_prep_layout pl;
   QAGNN_RETURN_IF(qagnn_graph_prep_layout(shape->N, shape->E, &pl));
+  const bool tiled = use_headtile(*shape);
+  if (tiled) QAGNN_RETURN_IF(zero_head_pads(*shape, (float*)workspace + W.qkm, (cudaStream_t)stream));
   return layer_forward(*shape, L, W, layer, x, extra, prep, pl, (const float*)folded, out, alpha_out, aggr_out,
-                       (float*)workspace, ACT_NONE, (cudaStream_t)stream);
+                       (float*)workspace, ACT_NONE, tiled, (cudaStream_t)stream);
 }
 
 extern "C" int32_t qagnn_node_feature_extra(const qagnn_shape* shape, const int64_t* node_type, const float* node_score,
@@ -226,11 +248,13 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   const float* f = (const float*)folded;
   float* extra = ws + W.extra;
   QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, extra, ws, st));
+  const bool tiled = use_headtile(s);
+  if (tiled) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
   const size_t ND = (size_t)s.N * s.D;
   const float* x = H_in;
   for (int l = 0; l < s.k; ++l) {  // mp_helper, :45-50 (dropout is the identity in eval)
     float* xo = x_layers_out ? x_layers_out + (size_t)l * ND : ws + ((l & 1) ? W.xb : W.xa);
-    QAGNN_RETURN_IF(layer_forward(s, L, W, l, x, extra, prep, pl, f, xo, nullptr, nullptr, ws, ACT_GELU, st));
+    QAGNN_RETURN_IF(layer_forward(s, L, W, l, x, extra, prep, pl, f, xo, nullptr, nullptr, ws, ACT_GELU, tiled, st));
     x = xo;
   }
   // output = GELU(Vh(H) + Vx(X))                                             (:92)

@@ -67,13 +67,15 @@ struct FoldLayout {
   size_t b1;         // [D]
   size_t w2;         // [D, D]   mlp.3 (copy)
   size_t b2;         // [D]
+  size_t keh;        // [H, C, DP] head-major zero-padded copy of ke (DP = d rounded up to 4)
+  size_t meh;        // [H, C, DP]
   size_t total;      // floats
 };
 FoldLayout make_fold_layout(const qagnn_shape& s);
 
 // ---- forward workspace ------------------------------------------------------------------------------
 struct WorkLayout {
-  size_t qkm;     // [N, 3D]
+  size_t qkm;     // [N, 3D]  or head-major [3, H, N, DP] for the tiled path
   size_t aggr;    // [N, D]
   size_t hmid;    // [N, D]
   size_t xa, xb;  // [N, D] ping-pong layer activations
@@ -88,10 +90,27 @@ WorkLayout make_work_layout(const qagnn_shape& s);
 // ---- kernels' host launchers (each returns a status) ------------------------------------------
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
+// Optional output remap of the projection GEMM for the shared-memory-tiled message passing:
+// logical column c of the [M, 3D] result (Q | Kx | Mx) is stored head-major and padded,
+//   C[ ((c / D) * H + (c % D) / d) * M * DP  +  r * DP  +  (c % D) % d ]        (pads are never written)
+struct HeadMajorOut {
+  int enabled, D, d, DP, H;
+};
+
 // C[M,N] (ldc) = act( [A1 | A2] @ W^T + bias ),  A1 [M,K1] (lda1), A2 [M,K2] (lda2) or null,
 // W [N, K1+K2] row-major (ldw).  bias may be null.
 int32_t sgemm_tn(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* W, int ldw,
-                 const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st);
+                 const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st,
+                 HeadMajorOut hm = HeadMajorOut{0, 0, 0, 0, 0});
+
+// ---- shared-memory-tiled message passing (mp_headtile.cu) ----------------------------------------------
+inline int head_dim_padded(int d) { return (d + 3) / 4 * 4; }
+// true when the per-head persistent kernel can run this shape on this device
+bool headtile_supported(const qagnn_shape& s);
+int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
+                                        const float* qkmh, const float* keh, const float* meh, float* score,
+                                        float* alpha, float* aggr, float* alpha_out, cudaStream_t st);
+int32_t zero_head_pads(const qagnn_shape& s, float* qkmh, cudaStream_t st);
 
 int32_t launch_message_passing(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
                                const float* qkm, const float* ke, const float* me, float* score, float* alpha,

@@ -39,6 +39,9 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   L.b1 = ltake(D);
   L.w2 = ltake(D * D);
   L.b2 = ltake(D);
+  const size_t DP = (size_t)head_dim_padded(s.D / s.H);
+  L.keh = ltake((size_t)s.H * C * DP);
+  L.meh = ltake((size_t)s.H * C * DP);
   L.layer_stride = lo;
   L.total = o + lo * (size_t)(s.k > 0 ? s.k : 0);
   return L;
@@ -130,6 +133,22 @@ __global__ void fold_mp_kernel(int D, int T, const float* __restrict__ tw, const
   }
 }
 
+// [C, D] -> head-major zero-padded [H, C, DP]
+__global__ void fold_head_major_kernel(int C, int D, int H, int DP, const float* __restrict__ ke,
+                                       const float* __restrict__ me, float* __restrict__ keh,
+                                       float* __restrict__ meh) {
+  const int d = D / H;
+  const int64_t total = (int64_t)H * C * DP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % DP);
+    const int c = (int)((i / DP) % C);
+    const int h = (int)(i / ((int64_t)DP * C));
+    const bool ok = j < d;
+    keh[i] = ok ? ke[(size_t)c * D + h * d + j] : 0.f;
+    meh[i] = ok ? me[(size_t)c * D + h * d + j] : 0.f;
+  }
+}
+
 }  // namespace
 }  // namespace qagnn
 
@@ -178,6 +197,11 @@ extern "C" int32_t qagnn_fold_weights(const qagnn_shape* shape, const qagnn_edge
     // edge part of linear_key / linear_msg: columns [2D,3D) of the [D,3D] weights
     QAGNN_RETURN_IF(sgemm_tn(f + L.tab, D, D, nullptr, 0, 0, p.key_w + 2 * D, 3 * D, p.key_b, lb + L.ke, D, C, D, ACT_NONE, st));
     QAGNN_RETURN_IF(sgemm_tn(f + L.tab, D, D, nullptr, 0, 0, p.msg_w + 2 * D, 3 * D, p.msg_b, lb + L.me, D, C, D, ACT_NONE, st));
+    const int DP = head_dim_padded(D / shape->H);
+    const int64_t nhm = (int64_t)shape->H * C * DP;
+    fold_head_major_kernel<<<(unsigned)((nhm + 255) / 256), 256, 0, st>>>(C, D, shape->H, DP, lb + L.ke, lb + L.me,
+                                                                          lb + L.keh, lb + L.meh);
+    QAGNN_CHECK_LAUNCH();
   }
   if (mp) {
     const int Dh = D / 2;

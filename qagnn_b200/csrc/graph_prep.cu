@@ -43,7 +43,7 @@ PrepScratch make_scratch(int64_t N, int64_t E) {
 }
 
 __global__ void prep_edges_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
-                                  const int64_t* __restrict__ node_type, int64_t N, int64_t E, int T, int R,
+                                  const int64_t* __restrict__ node_type, int64_t N, int64_t E, int T, int R, int npg,
                                   int32_t* __restrict__ src_o, int32_t* __restrict__ tgt_o,
                                   int32_t* __restrict__ combo_o, int32_t* __restrict__ cnt_src,
                                   int32_t* __restrict__ cnt_tgt, int32_t* __restrict__ status) {
@@ -57,6 +57,7 @@ __global__ void prep_edges_kernel(const int64_t* __restrict__ edge_index, const 
       r = edge_type[e];
       if (s < 0 || s >= N || t < 0 || t >= N) { bad |= 1; s = min(max(s, (int64_t)0), N - 1); t = min(max(t, (int64_t)0), N - 1); }
       if (r < 0 || r >= R) { bad |= 2; r = min(max(r, (int64_t)0), (int64_t)R - 1); }
+      if (npg > 0 && s / npg != t / npg) bad |= 8;  // edge crosses a sub-graph boundary
     } else {
       s = t = e - E;  // self loop, own type index R (:420-421)
       r = R;
@@ -187,24 +188,38 @@ __global__ void prep_sort_segments_kernel(int64_t N, const int32_t* __restrict__
 __global__ void prep_payload_src_kernel(int64_t Ep, const int32_t* __restrict__ perm_src,
                                         const int32_t* __restrict__ tgt, const int32_t* __restrict__ combo,
                                         int32_t* __restrict__ csr_src_tgt, int32_t* __restrict__ csr_src_combo,
-                                        int32_t* __restrict__ inv_src) {
+                                        int32_t* __restrict__ inv_src, const int32_t* __restrict__ src, int npg,
+                                        int32_t* __restrict__ pk_src) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x) {
     const int e = perm_src[p];
-    csr_src_tgt[p] = tgt[e];
-    csr_src_combo[p] = combo[e];
+    const int t = tgt[e], c = combo[e];
+    csr_src_tgt[p] = t;
+    csr_src_combo[p] = c;
     inv_src[e] = (int32_t)p;
+    if (npg > 0) {  // local target id | combo, for the shared-memory-tiled kernels
+      int tl = t - (src[e] / npg) * npg;
+      tl = min(max(tl, 0), npg - 1);
+      pk_src[p] = (int32_t)(((uint32_t)tl << 16) | ((uint32_t)c & 0xffffu));
+    }
   }
 }
 
 __global__ void prep_payload_tgt_kernel(int64_t Ep, const int32_t* __restrict__ perm_tgt,
                                         const int32_t* __restrict__ src, const int32_t* __restrict__ combo,
                                         const int32_t* __restrict__ inv_src, int32_t* __restrict__ csr_tgt_src,
-                                        int32_t* __restrict__ csr_tgt_combo, int32_t* __restrict__ csr_tgt_apos) {
+                                        int32_t* __restrict__ csr_tgt_combo, int32_t* __restrict__ csr_tgt_apos,
+                                        const int32_t* __restrict__ tgt, int npg, int32_t* __restrict__ pk_tgt) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x) {
     const int e = perm_tgt[p];
-    csr_tgt_src[p] = src[e];
-    csr_tgt_combo[p] = combo[e];
+    const int s = src[e], c = combo[e];
+    csr_tgt_src[p] = s;
+    csr_tgt_combo[p] = c;
     csr_tgt_apos[p] = inv_src[e];
+    if (npg > 0) {
+      int sl = s - (tgt[e] / npg) * npg;
+      sl = min(max(sl, 0), npg - 1);
+      pk_tgt[p] = (int32_t)(((uint32_t)sl << 16) | ((uint32_t)c & 0xffffu));
+    }
   }
 }
 
@@ -237,6 +252,8 @@ extern "C" int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layo
   out->csr_tgt_src = take(Ep);
   out->csr_tgt_combo = take(Ep);
   out->csr_tgt_apos = take(Ep);
+  out->pk_src = take(Ep);
+  out->pk_tgt = take(Ep);
   out->status = take(4);
   out->scratch = o;
   o += make_scratch(N, E).total * 4;
@@ -267,6 +284,10 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   int32_t* scr = I(pl.scratch);
   const int64_t Ep = N + E;
   const int nb = (int)scan_blocks(N);
+  // packed 16|16 local ids need n_per_graph and the combo count to fit in 16 bits
+  const int64_t Ccombo = (int64_t)(shape->R + 1) * shape->T * shape->T;
+  const int npg = (shape->n_per_graph > 0 && shape->n_per_graph <= 65535 && Ccombo <= 65536 &&
+                   N % shape->n_per_graph == 0) ? shape->n_per_graph : 0;
 
   ProfScope ps(QAGNN_PROF_GRAPH_PREP, st);
   // zero the status word and the count arrays (status .. cnt_tgt are contiguous up to bsum)
@@ -274,7 +295,7 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   QAGNN_CHECK_CUDA(cudaMemsetAsync(scr + sc.cnt_src, 0, (sc.bsum - sc.cnt_src) * 4, st));
 
   prep_edges_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(edge_index, edge_type, node_type, N, E, shape->T, shape->R,
-                                                       I(pl.src), I(pl.tgt), I(pl.combo), scr + sc.cnt_src,
+                                                       shape->n_per_graph > 0 ? shape->n_per_graph : 0, I(pl.src), I(pl.tgt), I(pl.combo), scr + sc.cnt_src,
                                                        scr + sc.cnt_tgt, I(pl.status));
   QAGNN_CHECK_LAUNCH();
   scan_block_sums_kernel<<<dim3(nb, 2), kScanChunk, 0, st>>>(scr + sc.cnt_src, scr + sc.cnt_tgt, N, scr + sc.bsum, nb);
@@ -293,11 +314,12 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   QAGNN_CHECK_LAUNCH();
   prep_payload_src_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_src), I(pl.tgt), I(pl.combo),
                                                              I(pl.csr_src_tgt), I(pl.csr_src_combo),
-                                                             scr + sc.inv_src);
+                                                             scr + sc.inv_src, I(pl.src), npg, I(pl.pk_src));
   QAGNN_CHECK_LAUNCH();
   prep_payload_tgt_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_tgt), I(pl.src), I(pl.combo),
                                                              scr + sc.inv_src, I(pl.csr_tgt_src),
-                                                             I(pl.csr_tgt_combo), I(pl.csr_tgt_apos));
+                                                             I(pl.csr_tgt_combo), I(pl.csr_tgt_apos), I(pl.tgt), npg,
+                                                             I(pl.pk_tgt));
   QAGNN_CHECK_LAUNCH();
   if (validate) {
     int32_t h = 0;

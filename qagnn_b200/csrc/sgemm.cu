@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(NT) sgemm_tn_kernel(const float* __restrict__ 
                                                       const float* __restrict__ A2, int lda2, int K2,
                                                       const float* __restrict__ W, int ldw,
                                                       const float* __restrict__ bias, float* __restrict__ C, int ldc,
-                                                      int64_t M, int N, int vecC) {
+                                                      int64_t M, int N, int vecC, HeadMajorOut hm) {
   __shared__ __align__(16) float As[2][BK][LDS];
   __shared__ __align__(16) float Ws[2][BK][LDS];
   const int K = K1 + K2;
@@ -125,7 +125,16 @@ __global__ void __launch_bounds__(NT) sgemm_tn_kernel(const float* __restrict__ 
         if (ACT == ACT_GELU) x = gelu_tanh(x);
         v[j] = x;
       }
-      if (vecC && c + 3 < N) {
+      if (hm.enabled) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = c + j;
+          if (cc < N) {
+            const int which = cc / hm.D, jd = cc % hm.D;
+            C[((size_t)(which * hm.H + jd / hm.d) * M + r) * hm.DP + jd % hm.d] = v[j];
+          }
+        }
+      } else if (vecC && c + 3 < N) {
         *reinterpret_cast<float4*>(C + r * ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
@@ -138,17 +147,18 @@ __global__ void __launch_bounds__(NT) sgemm_tn_kernel(const float* __restrict__ 
 
 template <bool VEC>
 int32_t launch(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* W, int ldw,
-               const float* bias, float* C, int ldc, int64_t M, int N, Act act, int vecC, cudaStream_t st) {
+               const float* bias, float* C, int ldc, int64_t M, int N, Act act, int vecC, cudaStream_t st,
+               HeadMajorOut hm) {
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
   switch (act) {
     case ACT_NONE:
-      sgemm_tn_kernel<VEC, ACT_NONE><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC);
+      sgemm_tn_kernel<VEC, ACT_NONE><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC, hm);
       break;
     case ACT_RELU:
-      sgemm_tn_kernel<VEC, ACT_RELU><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC);
+      sgemm_tn_kernel<VEC, ACT_RELU><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC, hm);
       break;
     case ACT_GELU:
-      sgemm_tn_kernel<VEC, ACT_GELU><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC);
+      sgemm_tn_kernel<VEC, ACT_GELU><<<grid, NT, 0, st>>>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, vecC, hm);
       break;
   }
   QAGNN_CHECK_LAUNCH();
@@ -160,15 +170,15 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace
 
 int32_t sgemm_tn(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* W, int ldw,
-                 const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st) {
+                 const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st, HeadMajorOut hm) {
   if (M <= 0 || N <= 0) return QAGNN_OK;
   if (!A1 || !W || !C || K1 <= 0 || (K2 > 0 && !A2)) return QAGNN_ERR_INVALID_ARGUMENT;
   if (K2 <= 0) { A2 = nullptr; lda2 = 0; K2 = 0; }
   const bool vec = aligned16(A1) && aligned16(W) && (lda1 % 4 == 0) && (ldw % 4 == 0) && (K1 % 4 == 0) &&
                    (K2 == 0 || (aligned16(A2) && lda2 % 4 == 0 && K2 % 4 == 0));
   const int vecC = aligned16(C) && (ldc % 4 == 0);
-  return vec ? launch<true>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, act, vecC, st)
-             : launch<false>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, act, vecC, st);
+  return vec ? launch<true>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, act, vecC, st, hm)
+             : launch<false>(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, C, ldc, M, N, act, vecC, st, hm);
 }
 
 }  // namespace qagnn

@@ -301,7 +301,7 @@ class QAGNN_Message_Passing(nn.Module):
             prep = GraphPrep(edge_index, edge_type, nt, self.n_ntype, self.n_etype, n, self.check_indices)
         if prep.N != B * n:
             raise ValueError("graph workspace was built for a different number of nodes")
-        shape = self._shape(B * n, prep.E, n)
+        shape = self._shape(B * n, prep.E, prep.n_per_graph)
         folded = self._folded.get(shape, self.edge_encoder, list(self.gnn_layers), self._mp_tensors(), dev)
         ws = self._ws.get(lib.qagnn_forward_workspace_bytes(C.byref(shape)), dev)
         out = torch.empty_like(Hc)

@@ -174,3 +174,36 @@ def test_cfg2_batch_independence_and_edge_permutation(cfg2):
     perm = torch.randperm(d["edge_index"].size(1), device=DEV, generator=torch.Generator(DEV).manual_seed(0))
     shuf = mod(d["H"], (d["edge_index"][:, perm], d["edge_type"][perm]), d["node_type"], d["node_score"])
     Hh.assert_close(shuf, full.cpu(), "edge permutation", atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("mp"))
+def test_tiled_and_csr_kernels_agree_and_match_golden(name):
+    """The shared-memory-tiled kernel (n_per_graph known) and the general CSR kernels compute the same layer;
+    both match the reference's alpha / x of layer 0."""
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sd = Hh.regen_mp_inputs(fx)
+    d = _dev(inp)
+    mod = _mp_module(c, fx, sd)
+    extra = mod.node_feature_extra(d["node_type"], d["node_score"])
+    X = d["H"].view(-1, c["D"]).contiguous()
+    nt = d["node_type"].view(-1)
+    layer = mod.gnn_layers[0]
+    prep_t = GraphPrep(d["edge_index"], d["edge_type"], nt, fx["n_ntype"], fx["n_etype"], n_per_graph=c["n"])
+    prep_c = GraphPrep(d["edge_index"], d["edge_type"], nt, fx["n_ntype"], fx["n_etype"], n_per_graph=0)
+    (out_t, (ei_t, al_t)), ag_t = layer(X, None, None, nt, extra, return_attention_weights=True, prep=prep_t, return_aggr=True)
+    (out_c, (ei_c, al_c)), ag_c = layer(X, None, None, nt, extra, return_attention_weights=True, prep=prep_c, return_aggr=True)
+    assert torch.equal(ei_t, ei_c)
+    Hh.assert_close(al_t, al_c.cpu(), "alpha tiled vs csr", atol=2e-6, rtol=2e-5)
+    Hh.assert_close(ag_t, ag_c.cpu(), "aggr tiled vs csr", atol=2e-5, rtol=2e-5)
+    Hh.assert_close(al_t, fx["layers"][0]["alpha"], "alpha tiled vs golden")
+    Hh.assert_close(mod.activation(out_t), fx["layers"][0]["x"], "x tiled vs golden")
+
+
+def test_cross_graph_edge_is_rejected_when_n_per_graph_is_given():
+    inp = O.synth_graph_batch(2, 10, 20, 64, 38, 0)
+    d = _dev(inp)
+    bad = d["edge_index"].clone(); bad[0, 0] = 0; bad[1, 0] = 15  # graph 0 -> graph 1
+    GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=0)  # legal for a general graph
+    with pytest.raises(IndexError):
+        GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=10)
