@@ -103,7 +103,7 @@ typedef struct qagnn_prep_layout {
   size_t total_bytes;
   size_t src;          /* [E'] source of edge e (self loops at e >= E)                */
   size_t tgt;          /* [E'] target of edge e                                       */
-  size_t combo;        /* [E'] (etype'*T + type[src])*T + type[tgt], etype' = R on self loops */
+  size_t combo;        /* [E'] (etype*T + type[src])*T + type[tgt]; self loop of v: R*T*T + type[v] */
   size_t rowptr_src;   /* [N+1] CSR by source; out-degree = rowptr_src[v+1]-rowptr_src[v] */
   size_t rowptr_tgt;   /* [N+1] CSR by target                                         */
   size_t perm_src;     /* [E'] edge ids stably sorted by source                        */
@@ -115,6 +115,7 @@ typedef struct qagnn_prep_layout {
   size_t csr_tgt_apos; /* [E'] position of edge perm_tgt[p] in the by-source order      */
   size_t pk_src;       /* [E'] (tgt - graph_base) << 16 | combo, by-source order (n_per_graph > 0 only) */
   size_t pk_tgt;       /* [E'] (src - graph_base) << 16 | combo, by-target order (n_per_graph > 0 only) */
+  size_t csr_src_tpos; /* [E'] position of edge perm_src[p] in the by-target order       */
   size_t status;       /* [4]  device-side error word + counters                        */
   size_t scratch;      /* internal                                                     */
 } qagnn_prep_layout;

@@ -249,8 +249,8 @@ def qagnn_decoder_forward(sd, sent_vecs, concept_ids, node_type_ids, node_scores
 # ----------------------------------------------------------------------------------------------
 def graph_prep_oracle(edge_index, edge_type, node_type, n_ntype, n_etype):
     """Index bookkeeping implied by modeling_qagnn.py:419-438,476-479:
-    edge_index' (self loops appended), combined one-hot position
-    combo = (etype'*T + type[src])*T + type[tgt] (etype' = n_etype on self loops), out-degree by
+    edge_index' (self loops appended), edge-feature index
+    combo = (etype*T + type[src])*T + type[tgt] (self loop of v: R*T*T + type[v]), out-degree by
     source, and the stable CSR orders by source / by target."""
     ei = edge_index.numpy().astype(np.int64)
     et = edge_type.numpy().astype(np.int64)
@@ -260,7 +260,10 @@ def graph_prep_oracle(edge_index, edge_type, node_type, n_ntype, n_etype):
     src = np.concatenate([ei[0], loop])
     tgt = np.concatenate([ei[1], loop])
     etp = np.concatenate([et, np.full(N, n_etype, dtype=np.int64)])
+    # index of the distinct one-hot edge feature: real edges (et, type[src], type[tgt]); self loops (type[v])
+    E_real = ei.shape[1]
     combo = (etp * n_ntype + nt[src]) * n_ntype + nt[tgt]
+    combo[E_real:] = n_etype * n_ntype * n_ntype + nt[src[E_real:]]
     outdeg = np.bincount(src, minlength=N).astype(np.int64)
     indeg = np.bincount(tgt, minlength=N).astype(np.int64)
     perm_src = np.argsort(src, kind="stable")

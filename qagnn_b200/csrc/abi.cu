@@ -63,8 +63,9 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   W.xb = take(N * D);
   W.extra = take(N * D);
   W.sinb = take(N * (D / 2));
-  W.score = take(Ep * H);
-  W.alpha = take(Ep * H);
+  const size_t Eps = (Ep + 3) / 4 * 4;  // per-head stride of the tiled path
+  W.score = take(Eps * H);
+  W.alpha = take(Eps * H);
   W.total = o;
   return W;
 }

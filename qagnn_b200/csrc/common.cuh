@@ -45,7 +45,7 @@ struct ProfScope {
 };
 
 // ---- folded-weight blob ---------------------------------------------------------------------------
-// All offsets in floats from the start of the blob.  C = (R+1)*T*T rows in the edge tables.
+// All offsets in floats from the start of the blob.  C = R*T*T + T rows in the edge tables.
 struct FoldLayout {
   int D, H, T, R, k, C;
   size_t tab;        // [C, D]   edge_encoder(onehot(c))                      (layer-invariant)

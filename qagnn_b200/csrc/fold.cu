@@ -1,6 +1,6 @@
 // Weight folding: turns the reference's parameters (state_dict layout) into what the node-level
 // formulation needs (SURVEY.md §8a "exact per-layer math"):
-//   tab[c]  = edge_encoder(onehot(c)), c in [0,(R+1)*T*T)      modeling_qagnn.py:30,419-433  (layer-invariant)
+//   tab[c]  = edge_encoder(onehot(c)), c in [0, R*T*T + T)      modeling_qagnn.py:30,419-433  (layer-invariant)
 //   Ke, Me  = tab @ W_k[:,2D:]^T + b_k,  tab @ W_m[:,2D:]^T + b_m  (edge part of linear_key/linear_msg :464-465)
 //   Wp      = [W_q/sqrt(d) ; W_k[:,:2D] ; W_m[:,:2D]]            (node part, one [3D,2D] projection :464-466,469)
 //   W1',b1' = BatchNorm1d(eval) folded into mlp.0                  (:408)
@@ -16,7 +16,7 @@ namespace qagnn {
 FoldLayout make_fold_layout(const qagnn_shape& s) {
   FoldLayout L;
   L.D = s.D; L.H = s.H; L.T = s.T; L.R = s.R; L.k = s.k;
-  L.C = (s.R + 1) * s.T * s.T;
+  L.C = s.R * s.T * s.T + s.T;  // R*T*T real-edge combos + T self-loop combos
   const size_t D = s.D, C = L.C, Dh = s.D / 2;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n * 4) / 4; return r; };
@@ -56,7 +56,8 @@ __global__ void fold_edge_hidden_kernel(int C, int D, int T, int R, const float*
   const int F = R + 1 + 2 * T;  // width of the reference's one-hot edge feature
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)C * D; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i / D), f = (int)(i % D);
-    const int r = c / (T * T), ts = (c / T) % T, tt = c % T;
+    int r = c / (T * T), ts = (c / T) % T, tt = c % T;
+    if (c >= R * T * T) { r = R; ts = tt = c - R * T * T; }  // self loop of a type-ts node (:420-429)
     const float* w = w0 + (size_t)f * F;
     float pre = ((w[r] + w[R + 1 + ts]) + w[R + 1 + T + tt]) + b0[f];
     float y = (pre - mean[f]) / sqrtf(var[f] + 1e-5f) * g[f] + beta[f];

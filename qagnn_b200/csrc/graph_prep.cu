@@ -2,8 +2,9 @@
 // 476-479), done once per forward and reused by all k layers.
 //
 //   edge_index' = [edge_index | self loops]                                   (:436-438)
-//   combo[e]    = (etype'[e]*T + type[src])*T + type[tgt]   — the position of the single 1-triple
-//                 in the reference's [E', R+1+2T] one-hot edge feature         (:419-432)
+//   combo[e]    = (etype*T + type[src])*T + type[tgt] for real edges, R*T*T + type[v] for the self loop of
+//                 v — an index of the distinct values the reference's [E', R+1+2T] one-hot edge feature can
+//                 take (:419-432); C = R*T*T + T rows in the folded edge tables
 //   out-degree by source (self loop included)                                  (:476-479)
 //   stable CSR orders by source (softmax groups, :472) and by target (aggregation, :442)
 //
@@ -20,6 +21,7 @@ struct PrepScratch {
   size_t bsum;              // [2 * nb]
   size_t tmp_src, tmp_tgt;  // [E'] unsorted CSR fill
   size_t inv_src;           // [E'] edge id -> position in the by-source order
+  size_t inv_tgt;           // [E'] edge id -> position in the by-target order
   size_t total;             // int32 words
 };
 
@@ -38,6 +40,7 @@ PrepScratch make_scratch(int64_t N, int64_t E) {
   s.tmp_src = take(Ep);
   s.tmp_tgt = take(Ep);
   s.inv_src = take(Ep);
+  s.inv_tgt = take(Ep);
   s.total = o;
   return s;
 }
@@ -68,7 +71,7 @@ __global__ void prep_edges_kernel(const int64_t* __restrict__ edge_index, const 
     if (bad) atomicOr(status, bad);
     src_o[e] = (int32_t)s;
     tgt_o[e] = (int32_t)t;
-    combo_o[e] = (int32_t)((r * T + ts) * T + tt);
+    combo_o[e] = (e < E) ? (int32_t)((r * T + ts) * T + tt) : (int32_t)((int64_t)R * T * T + ts);
     atomicAdd(cnt_src + s, 1);
     atomicAdd(cnt_tgt + t, 1);
   }
@@ -208,10 +211,12 @@ __global__ void prep_payload_tgt_kernel(int64_t Ep, const int32_t* __restrict__ 
                                         const int32_t* __restrict__ src, const int32_t* __restrict__ combo,
                                         const int32_t* __restrict__ inv_src, int32_t* __restrict__ csr_tgt_src,
                                         int32_t* __restrict__ csr_tgt_combo, int32_t* __restrict__ csr_tgt_apos,
-                                        const int32_t* __restrict__ tgt, int npg, int32_t* __restrict__ pk_tgt) {
+                                        const int32_t* __restrict__ tgt, int npg, int32_t* __restrict__ pk_tgt,
+                                        int32_t* __restrict__ inv_tgt) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x) {
     const int e = perm_tgt[p];
     const int s = src[e], c = combo[e];
+    inv_tgt[e] = (int32_t)p;
     csr_tgt_src[p] = s;
     csr_tgt_combo[p] = c;
     csr_tgt_apos[p] = inv_src[e];
@@ -221,6 +226,12 @@ __global__ void prep_payload_tgt_kernel(int64_t Ep, const int32_t* __restrict__ 
       pk_tgt[p] = (int32_t)(((uint32_t)sl << 16) | ((uint32_t)c & 0xffffu));
     }
   }
+}
+
+__global__ void prep_tpos_kernel(int64_t Ep, const int32_t* __restrict__ perm_src, const int32_t* __restrict__ inv_tgt,
+                                 int32_t* __restrict__ csr_src_tpos) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < Ep; p += (int64_t)gridDim.x * blockDim.x)
+    csr_src_tpos[p] = inv_tgt[perm_src[p]];
 }
 
 inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
@@ -254,6 +265,7 @@ extern "C" int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layo
   out->csr_tgt_apos = take(Ep);
   out->pk_src = take(Ep);
   out->pk_tgt = take(Ep);
+  out->csr_src_tpos = take(Ep);
   out->status = take(4);
   out->scratch = o;
   o += make_scratch(N, E).total * 4;
@@ -285,7 +297,7 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   const int64_t Ep = N + E;
   const int nb = (int)scan_blocks(N);
   // packed 16|16 local ids need n_per_graph and the combo count to fit in 16 bits
-  const int64_t Ccombo = (int64_t)(shape->R + 1) * shape->T * shape->T;
+  const int64_t Ccombo = (int64_t)shape->R * shape->T * shape->T + shape->T;
   const int npg = (shape->n_per_graph > 0 && shape->n_per_graph <= 65535 && Ccombo <= 65536 &&
                    N % shape->n_per_graph == 0) ? shape->n_per_graph : 0;
 
@@ -319,7 +331,9 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   prep_payload_tgt_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_tgt), I(pl.src), I(pl.combo),
                                                              scr + sc.inv_src, I(pl.csr_tgt_src),
                                                              I(pl.csr_tgt_combo), I(pl.csr_tgt_apos), I(pl.tgt), npg,
-                                                             I(pl.pk_tgt));
+                                                             I(pl.pk_tgt), scr + sc.inv_tgt);
+  QAGNN_CHECK_LAUNCH();
+  prep_tpos_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_src), scr + sc.inv_tgt, I(pl.csr_src_tpos));
   QAGNN_CHECK_LAUNCH();
   if (validate) {
     int32_t h = 0;

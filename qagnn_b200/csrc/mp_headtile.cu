@@ -5,15 +5,19 @@
 //
 // Why this shape (profiles/r1_microbench.txt, profiles/r1_v1_mp_ncu.md): each edge needs four row
 // gathers (Kx[tgt], Ke[combo], Mx[src], Me[combo]); served from L2 they cap at ~11 G rows/s, so the
-// per-head slice of the edge tables (C x d floats, 125 KB at C=624, d=50) has to live in shared
+// per-head slice of the edge tables (C x d floats, 127 KB at C=612, d=50) has to live in shared
 // memory next to the node tile of the current graph.  Hence:
 //   * grid = H x floor(#SM / H) persistent CTAs; CTA (h, slot) owns head h of graphs slot, slot+S, ...
-//   * phase 1: Ke_h resident, Kx_h tiles of its graphs streamed through a 2-deep TMA (cp.async.bulk)
-//     ring -> raw logits, online softmax per source node, rescaled weights a'[e] to global (L2);
-//   * phase 2: Me_h swapped in, Mx_h tiles streamed the same way -> aggr[:, h*d:(h+1)*d].
-//   * 8 lanes per node (quarter-warp), each lane owning float4 chunks l, l+8 of the padded head row:
-//     a quarter-warp LDS.128 reads 128 contiguous bytes = one conflict-free wavefront; the dot
-//     product needs 3 shuffles; the softmax is carried online in registers (no extra pass).
+//   * phase 1: Ke_h resident, Kx_h tiles streamed through a 2-deep TMA (cp.async.bulk) ring ->
+//     logits, softmax per source node, rescaled weights a'[e] written in BY-TARGET order (L2);
+//   * phase 2: Me_h swapped in, Mx_h tiles streamed the same way -> aggr[:, h*d:(h+1)*d];
+//   * a loader warp runs one graph ahead of the consumers: it issues the TMA copies and stages the
+//     graph's CSR slice (row pointers, packed local ids, phase-2 weights) into shared memory, so the
+//     consumers' inner loops touch no global memory (the v2 kernel lost >50 % to L2 latency there);
+//   * consumers: 8 lanes per node (quarter-warp), each lane owning float4 chunks l, l+8 of the padded
+//     head row: a quarter-warp LDS.128 covers 128 contiguous bytes = one conflict-free wavefront;
+//     packed FP32x2 math (FADD2/FFMA2, sm_100a); the dot product needs 3 shuffles; two edges per
+//     iteration for ILP; the softmax runs lane-parallel over the node's edges after the loop.
 // Node rows come from the head-major padded projection layout [3][H][N][DP] written by the
 // projection GEMM, so a tile is one contiguous n*DP*4-byte bulk copy.
 #include "common.cuh"
@@ -23,9 +27,9 @@ namespace qagnn {
 namespace {
 
 struct HeadTileParams {
-  int64_t N, Ep;
-  int n, G, H, D, d, DP, C, S, W;
-  const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *pk_tgt, *apos, *perm_src;
+  int64_t N, Eps;  // Eps = per-head stride of score/alpha (E' rounded up to 4)
+  int n, G, H, D, d, DP, C, S, W, ecap;
+  const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *pk_tgt, *tpos, *perm_src;
   const float *qkmh, *keh, *meh;
   float *score, *alpha, *aggr, *alpha_out;
 };
@@ -60,30 +64,45 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// large copies are split so that a single transaction count stays far below the 2^20-1 limit
 __device__ __forceinline__ void bulk_g2s_chunked(char* dst, const char* src, uint32_t bytes, uint64_t* bar) {
   mbar_expect_tx(bar, bytes);
   const uint32_t kChunk = 32768;
   for (uint32_t o = 0; o < bytes; o += kChunk) bulk_g2s(dst + o, src + o, min(kChunk, bytes - o), bar);
 }
 
-__device__ __forceinline__ float dot4(const float4& q, const float4& a, const float4& b) {
-  return q.x * (a.x + b.x) + q.y * (a.y + b.y) + q.z * (a.z + b.z) + q.w * (a.w + b.w);
-}
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
-template <int CPL>
-__global__ void __launch_bounds__(1024, 1) mp_headtile_kernel(const HeadTileParams p) {
+// shared-memory carve-up (bytes from the start of dynamic smem)
+struct SmemMap {
+  uint32_t tab, tile0, tile_bytes, rp0, rp_bytes, ia0, ib0, idx_bytes, bars, meta;
+};
+__host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap) {
+  SmemMap m;
+  m.tab = 0;
+  m.tile0 = (uint32_t)C * DP * 4;
+  m.tile_bytes = (uint32_t)n * DP * 4;
+  m.rp0 = m.tile0 + 2 * m.tile_bytes;
+  m.rp_bytes = (uint32_t)((n + 1 + 3) / 4 * 4) * 4;
+  m.ia0 = m.rp0 + 2 * m.rp_bytes;
+  m.idx_bytes = (uint32_t)ecap * 4;
+  m.ib0 = m.ia0 + 2 * m.idx_bytes;
+  m.bars = m.ib0 + 2 * m.idx_bytes;
+  m.meta = m.bars + 5 * 8;
+  return m;
+}
+inline size_t smem_total(const SmemMap& m) { return (size_t)m.meta + 4 * 4 + 16; }
+
+template <int CPL, int QPW>  // float4 chunks per lane; node-quads per consumer warp and graph (1 or 2)
+__global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(const HeadTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NCH = p.DP / 4;
-  float4* tab = reinterpret_cast<float4*>(smem_raw);
-  const size_t tab_bytes = (size_t)p.C * p.DP * 4;
-  const size_t tile_bytes = (size_t)p.n * p.DP * 4;
-  float4* tile[2] = {reinterpret_cast<float4*>(smem_raw + tab_bytes),
-                     reinterpret_cast<float4*>(smem_raw + tab_bytes + tile_bytes)};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + 2 * tile_bytes);
-  uint64_t* full = bars;        // [2]
-  uint64_t* empty = bars + 2;   // [2]
+  const SmemMap sm = make_smem_map(p.C, p.DP, p.n, p.ecap);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.bars);
+  uint64_t* full = bars;        // [2]  1 expect_tx arrival (tile) + 1 arrival (staged indices)
+  uint64_t* empty = bars + 2;   // [2]  W consumer arrivals
   uint64_t* tabbar = bars + 4;  // [1]
+  volatile int* meta = reinterpret_cast<volatile int*>(smem_raw + sm.meta);  // [2][2] = {base, staged}
 
   const int h = blockIdx.x % p.H;
   const int slot = blockIdx.x / p.H;
@@ -92,8 +111,8 @@ __global__ void __launch_bounds__(1024, 1) mp_headtile_kernel(const HeadTilePara
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(&full[0], 2);
+    mbar_init(&full[1], 2);
     mbar_init(&empty[0], p.W);
     mbar_init(&empty[1], p.W);
     mbar_init(tabbar, 1);
@@ -105,24 +124,54 @@ __global__ void __launch_bounds__(1024, 1) mp_headtile_kernel(const HeadTilePara
   const float* Qh = p.qkmh + (size_t)(0 * p.H + h) * head_rows;
   const float* Kh = p.qkmh + (size_t)(1 * p.H + h) * head_rows;
   const float* Mh = p.qkmh + (size_t)(2 * p.H + h) * head_rows;
+  const size_t hE = (size_t)h * p.Eps;
 
   if (warp == p.W) {
-    // ===================== producer warp: one lane drives the TMA ring =====================
-    if (lane == 0) {
-      bulk_g2s_chunked((char*)tab, (const char*)(p.keh + (size_t)h * p.C * p.DP), (uint32_t)tab_bytes, tabbar);
-      for (int t = 0; t < 2 * Gc; ++t) {
-        const int b = t & 1;
-        if (t == Gc) {
-          // phase switch: every consumer has left phase 1 once the last two tiles are released
-          mbar_wait(&empty[(Gc - 1) & 1], ((Gc - 1) >> 1) & 1);
-          if (Gc >= 2) mbar_wait(&empty[(Gc - 2) & 1], ((Gc - 2) >> 1) & 1);
-          bulk_g2s_chunked((char*)tab, (const char*)(p.meh + (size_t)h * p.C * p.DP), (uint32_t)tab_bytes, tabbar);
-        }
-        if (t >= 2) mbar_wait(&empty[b], ((t >> 1) - 1) & 1);
-        const int g = slot + (t < Gc ? t : t - Gc) * p.S;
-        const float* src = (t < Gc ? Kh : Mh) + (size_t)g * p.n * p.DP;
-        bulk_g2s_chunked((char*)tile[b], (const char*)src, (uint32_t)tile_bytes, &full[b]);
+    // ============ loader warp: TMA ring + CSR slice staging, one graph ahead of the consumers ============
+    if (lane == 0)
+      bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.keh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
+    for (int t = 0; t < 2 * Gc; ++t) {
+      const int b = t & 1;
+      const bool ph2 = t >= Gc;
+      if (t == Gc) {
+        // phase switch: every consumer has left phase 1 once the last two tiles are released
+        mbar_wait(&empty[(Gc - 1) & 1], ((Gc - 1) >> 1) & 1);
+        if (Gc >= 2) mbar_wait(&empty[(Gc - 2) & 1], ((Gc - 2) >> 1) & 1);
+        if (lane == 0)
+          bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.meh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
       }
+      if (t >= 2) mbar_wait(&empty[b], ((t >> 1) - 1) & 1);
+      const int g = slot + (ph2 ? t - Gc : t) * p.S;
+      if (lane == 0) {
+        const float* src = (ph2 ? Mh : Kh) + (size_t)g * p.n * p.DP;
+        bulk_g2s_chunked((char*)(smem_raw + sm.tile0 + b * sm.tile_bytes), (const char*)src, sm.tile_bytes, &full[b]);
+      }
+      // CSR slice of graph g in the order this phase walks (by source / by target)
+      const int32_t* rowptr = (ph2 ? p.rowptr_tgt : p.rowptr_src) + (size_t)g * p.n;
+      const int seg_beg = rowptr[0], seg_end = rowptr[p.n];
+      const int base = seg_beg & ~3;
+      const int cnt = seg_end - base;
+      const bool staged = cnt <= p.ecap;
+      int* rp = reinterpret_cast<int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
+      for (int i = lane; i <= p.n; i += 32) rp[i] = rowptr[i] - base;
+      if (staged) {
+        const int nvec = (cnt + 3) >> 2;
+        int4* ia = reinterpret_cast<int4*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
+        int4* ib = reinterpret_cast<int4*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
+        const int4* ga = reinterpret_cast<const int4*>((ph2 ? p.pk_tgt : p.pk_src) + base);
+        const int4* gb = ph2 ? reinterpret_cast<const int4*>(p.alpha + hE + base)
+                             : reinterpret_cast<const int4*>(p.tpos + base);
+        for (int i = lane; i < nvec; i += 32) {
+          ia[i] = ga[i];
+          ib[i] = gb[i];
+        }
+      }
+      if (lane == 0) {
+        meta[2 * b] = base;
+        meta[2 * b + 1] = staged ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[b]);
     }
     return;
   }
@@ -130,63 +179,115 @@ __global__ void __launch_bounds__(1024, 1) mp_headtile_kernel(const HeadTilePara
   // ========================= consumer warps: 4 nodes per warp, 8 lanes per node =========================
   const int l8 = lane & 7, qbase = lane & 24, qi = lane >> 3;
   const int nquads = (p.n + 3) / 4;
+  int chunk[CPL];
   bool cvalid[CPL];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) cvalid[k] = (l8 + 8 * k) < NCH;
-  const size_t hEp = (size_t)h * p.Ep;
+  for (int k = 0; k < CPL; ++k) {
+    cvalid[k] = (l8 + 8 * k) < NCH;
+    chunk[k] = cvalid[k] ? l8 + 8 * k : 0;  // idle lanes re-read chunk 0 (finite data) against q = 0
+  }
+  const float4* tab = reinterpret_cast<const float4*>(smem_raw + sm.tab);
+
+  auto load_q = [&](int g, int quad, float4 (&q)[CPL]) {
+    const int vl = quad * 4 + qi;
+    const int64_t v = (int64_t)g * p.n + (vl < p.n ? vl : 0);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      q[k] = (cvalid[k] && quad < nquads) ? __ldg(reinterpret_cast<const float4*>(Qh + v * p.DP) + chunk[k])
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
 
   // ---------------------------------- phase 1: attention weights ----------------------------------
+  float4 qn[QPW][CPL];  // Q rows of this warp's quads, prefetched one graph ahead
+#pragma unroll
+  for (int u = 0; u < QPW; ++u) load_q(slot, warp + u * p.W, qn[u]);
   mbar_wait(tabbar, 0);
   for (int t = 0; t < Gc; ++t) {
     const int b = t & 1;
     const int g = slot + t * p.S;
+    float4 qc[QPW][CPL];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) qc[u][k] = qn[u][k];
+    if (t + 1 < Gc) {
+#pragma unroll
+      for (int u = 0; u < QPW; ++u) load_q(g + p.S, warp + u * p.W, qn[u]);
+    }
     mbar_wait(&full[b], (t >> 1) & 1);
-    const float4* kt = tile[b];
-    for (int quad = warp; quad < nquads; quad += p.W) {
+    const float4* kt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
+    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
+    const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
+    const int* ib = reinterpret_cast<const int*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
+    const int base = meta[2 * b];
+    const bool staged = meta[2 * b + 1] != 0;
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+      const int quad = warp + u * p.W;
+      if (quad >= nquads) break;
       const int vl = quad * 4 + qi;
       const bool nvalid = vl < p.n;
-      const int64_t v = (int64_t)g * p.n + (nvalid ? vl : 0);
-      const int beg = p.rowptr_src[v];
-      const int deg = nvalid ? p.rowptr_src[v + 1] - beg : 0;
+      const int begr = rp[nvalid ? vl : 0];
+      const int deg = nvalid ? rp[vl + 1] - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
-      float4 q[CPL];
-#pragma unroll
-      for (int k = 0; k < CPL; ++k)
-        q[k] = cvalid[k] ? *reinterpret_cast<const float4*>(Qh + v * p.DP + 4 * (l8 + 8 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float m = -INFINITY, ssum = 0.f, skeep = 0.f;
+      float skeep = -INFINITY;  // lane j keeps the logit of edge j (j < 8)
       for (int i0 = 0; i0 < maxdeg; i0 += 8) {
-        const int pkv = (i0 + l8 < deg) ? p.pk_src[beg + i0 + l8] : 0;
+        int pkv = 0;
+        if (i0 + l8 < deg) pkv = staged ? ia[begr + i0 + l8] : p.pk_src[base + begr + i0 + l8];
         const int lim = min(8, maxdeg - i0);
-        for (int j = 0; j < lim; ++j) {
-          const uint32_t w = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
-          const float4* kr = kt + (size_t)(w >> 16) * NCH;
-          const float4* er = tab + (size_t)(w & 0xffffu) * NCH;
-          float s = 0.f;
+        for (int j = 0; j < lim; j += 2) {
+          const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
+          const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
+          const float4* k0 = kt + (w0 >> 16) * NCH;
+          const float4* e0 = tab + (w0 & 0xffffu) * NCH;
+          const float4* k1 = kt + (w1 >> 16) * NCH;
+          const float4* e1 = tab + (w1 & 0xffffu) * NCH;
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int k = 0; k < CPL; ++k)
-            if (cvalid[k]) s += dot4(q[k], kr[l8 + 8 * k], er[l8 + 8 * k]);
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          if (i0 + j < deg) {
-            // online softmax: one exp per edge
-            const float e = __expf(-fabsf(s - m));
-            if (s <= m) { ssum += e; } else { ssum = ssum * e + 1.f; m = s; }
-            if (l8 == j) {
-              if (i0 == 0) skeep = s; else p.score[hEp + beg + i0 + j] = s;
-            }
+          for (int k = 0; k < CPL; ++k) {
+            const float4 x0 = k0[chunk[k]], y0 = e0[chunk[k]], x1 = k1[chunk[k]], y1 = e1[chunk[k]];
+            a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[u][k]), a0);
+            a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[u][k]), a0);
+            a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[u][k]), a1);
+            a1 = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), hi2(qc[u][k]), a1);
+          }
+          float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 4);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          if (i0 == 0) {
+            skeep = (l8 == j) ? s0 : skeep;
+            skeep = (l8 == j + 1) ? s1 : skeep;
+          } else {  // hub nodes (degree > 8): spill the logits to the L2 scratch
+            if (l8 == 0 && i0 + j < deg) p.score[hE + base + begr + i0 + j] = s0;
+            if (l8 == 1 && i0 + j + 1 < deg) p.score[hE + base + begr + i0 + j + 1] = s1;
           }
         }
       }
+      // softmax over this node's out-edges, lane-parallel (lane j <-> edge j, j + 8, ...)
       if (maxdeg > 8) __syncwarp();
+      float m = (l8 < deg) ? skeep : -INFINITY;
+      for (int j = 8 + l8; j < deg; j += 8) m = fmaxf(m, p.score[hE + base + begr + j]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      float ex0 = (l8 < deg) ? expf(skeep - m) : 0.f;
+      float ssum = ex0;
+      for (int j = 8 + l8; j < deg; j += 8) ssum += expf(p.score[hE + base + begr + j] - m);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
       const float denom = ssum + 1e-16f;  // torch_geometric.utils.softmax
-      const float degf = (float)deg;
+      const float degf = (float)deg;      // out-degree of the source, self loop included (:476-481)
       for (int j = l8; j < deg; j += 8) {
-        const float s = j < 8 ? skeep : p.score[hEp + beg + j];
-        const float a = expf(s - m) / denom;
-        p.alpha[hEp + beg + j] = a * degf;  // rescale by the out-degree of the source (:476-481)
-        if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[beg + j] * p.H + h] = a;
+        const float a = (j < 8 ? ex0 : expf(p.score[hE + base + begr + j] - m)) / denom;
+        const int tp = staged ? ib[begr + j] : p.tpos[base + begr + j];
+        p.alpha[hE + tp] = a * degf;  // stored in by-target order for phase 2
+        if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[base + begr + j] * p.H + h] = a;
       }
     }
     __threadfence_block();
@@ -200,59 +301,69 @@ __global__ void __launch_bounds__(1024, 1) mp_headtile_kernel(const HeadTilePara
     const int b = t & 1;
     const int g = slot + (t - Gc) * p.S;
     mbar_wait(&full[b], (t >> 1) & 1);
-    const float4* mt = tile[b];
-    for (int quad = warp; quad < nquads; quad += p.W) {
+    const float4* mt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
+    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
+    const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
+    const float* ib = reinterpret_cast<const float*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
+    const int base = meta[2 * b];
+    const bool staged = meta[2 * b + 1] != 0;
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+      const int quad = warp + u * p.W;
+      if (quad >= nquads) break;
       const int vl = quad * 4 + qi;
       const bool nvalid = vl < p.n;
-      const int64_t v = (int64_t)g * p.n + (nvalid ? vl : 0);
-      const int beg = p.rowptr_tgt[v];
-      const int deg = nvalid ? p.rowptr_tgt[v + 1] - beg : 0;
+      const int begr = rp[nvalid ? vl : 0];
+      const int deg = nvalid ? rp[vl + 1] - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
-      float4 acc[CPL];
+      float2 acc[CPL][2];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < CPL; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
       for (int i0 = 0; i0 < maxdeg; i0 += 8) {
         int pkv = 0;
         float wv = 0.f;
         if (i0 + l8 < deg) {
-          pkv = p.pk_tgt[beg + i0 + l8];
-          wv = p.alpha[hEp + p.apos[beg + i0 + l8]];
+          pkv = staged ? ia[begr + i0 + l8] : p.pk_tgt[base + begr + i0 + l8];
+          wv = staged ? ib[begr + i0 + l8] : p.alpha[hE + base + begr + i0 + l8];
         }
         const int lim = min(8, maxdeg - i0);
-        for (int j = 0; j < lim; ++j) {
-          const uint32_t w = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
-          const float a = __shfl_sync(0xffffffffu, wv, qbase + j);  // 0 beyond this node's degree
-          const float4* mr = mt + (size_t)(w >> 16) * NCH;
-          const float4* er = tab + (size_t)(w & 0xffffu) * NCH;
+        for (int j = 0; j < lim; j += 2) {
+          const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
+          const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
+          const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);      // 0 beyond this node's degree
+          const float a1 = __shfl_sync(0xffffffffu, wv, qbase + j + 1);
+          const float4* m0 = mt + (w0 >> 16) * NCH;
+          const float4* e0 = tab + (w0 & 0xffffu) * NCH;
+          const float4* m1 = mt + (w1 >> 16) * NCH;
+          const float4* e1 = tab + (w1 & 0xffffu) * NCH;
+          const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
-            if (cvalid[k]) {
-              const float4 x = mr[l8 + 8 * k], y = er[l8 + 8 * k];
-              acc[k].x += (x.x + y.x) * a;
-              acc[k].y += (x.y + y.y) * a;
-              acc[k].z += (x.z + y.z) * a;
-              acc[k].w += (x.w + y.w) * a;
-            }
+            const float4 x0 = m0[chunk[k]], y0 = e0[chunk[k]], x1 = m1[chunk[k]], y1 = e1[chunk[k]];
+            acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
+            acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
+            acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
+            acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), aa1, acc[k][1]);
           }
         }
       }
       if (nvalid) {
-        float* out = p.aggr + v * p.D + (size_t)h * p.d;
+        float* out = p.aggr + ((int64_t)g * p.n + vl) * p.D + (size_t)h * p.d;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           const int c0 = 4 * (l8 + 8 * k);
           if (!cvalid[k] || c0 >= p.d) continue;
           if ((p.d & 3) == 0 && (p.D & 3) == 0) {
-            *reinterpret_cast<float4*>(out + c0) = acc[k];
+            *reinterpret_cast<float4*>(out + c0) = make_float4(acc[k][0].x, acc[k][0].y, acc[k][1].x, acc[k][1].y);
           } else if ((p.d & 1) == 0) {
-            *reinterpret_cast<float2*>(out + c0) = make_float2(acc[k].x, acc[k].y);
-            if (c0 + 2 < p.d) *reinterpret_cast<float2*>(out + c0 + 2) = make_float2(acc[k].z, acc[k].w);
+            *reinterpret_cast<float2*>(out + c0) = acc[k][0];
+            if (c0 + 2 < p.d) *reinterpret_cast<float2*>(out + c0 + 2) = acc[k][1];
           } else {
-            out[c0] = acc[k].x;
-            if (c0 + 1 < p.d) out[c0 + 1] = acc[k].y;
-            if (c0 + 2 < p.d) out[c0 + 2] = acc[k].z;
-            if (c0 + 3 < p.d) out[c0 + 3] = acc[k].w;
+            out[c0] = acc[k][0].x;
+            if (c0 + 1 < p.d) out[c0 + 1] = acc[k][0].y;
+            if (c0 + 2 < p.d) out[c0 + 2] = acc[k][1].x;
+            if (c0 + 3 < p.d) out[c0 + 3] = acc[k][1].y;
           }
         }
       }
@@ -270,7 +381,7 @@ __global__ void zero_head_pads_kernel(int64_t rows, int d, int DP, float* __rest
 
 struct HeadTilePlan {
   bool ok;
-  int DP, C, S, W, cpl, sms;
+  int DP, C, S, W, cpl, qpw, sms, ecap;
   size_t smem;
 };
 
@@ -280,22 +391,49 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   if (s.n_per_graph <= 0 || s.n_per_graph > 65535 || s.N % s.n_per_graph != 0) return pl;
   const int d = s.D / s.H;
   pl.DP = head_dim_padded(d);
-  pl.C = (s.R + 1) * s.T * s.T;
+  pl.C = s.R * s.T * s.T + s.T;
   if (pl.C > 65536 || pl.DP > 64) return pl;
   pl.cpl = pl.DP <= 32 ? 1 : 2;
-  int dev = 0, sms = 0, max_smem = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return pl;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  static int sms = 0, max_smem = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return pl;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   pl.sms = sms;
-  pl.smem = (size_t)pl.C * pl.DP * 4 + 2 * (size_t)s.n_per_graph * pl.DP * 4 + 64;
-  if (pl.smem > (size_t)max_smem || s.H > sms) return pl;
+  if (s.H > sms) return pl;
+  // index staging capacity: whatever is left after the table and the two tiles, at least a few edges per node
+  const SmemMap m0 = make_smem_map(pl.C, pl.DP, s.n_per_graph, 0);
+  const long fixed = (long)smem_total(m0);
+  long ecap = ((long)max_smem - fixed) / 16;  // 2 buffers x (ia + ib) x 4 bytes
+  ecap = ecap / 4 * 4;
+  if (ecap < 2 * (long)s.n_per_graph + 8) return pl;
+  if (ecap > 65536) ecap = 65536;
+  pl.ecap = (int)ecap;
+  pl.smem = smem_total(make_smem_map(pl.C, pl.DP, s.n_per_graph, pl.ecap));
   pl.S = sms / s.H;
   const int quads = (s.n_per_graph + 3) / 4;
-  const int passes = (quads + 30) / 31;  // at most 31 consumer warps + 1 producer warp
+  const int passes = (quads + 30) / 31;  // at most 31 consumer warps + 1 loader warp
+  if (passes > 2) return pl;
+  pl.qpw = passes;
   pl.W = (quads + passes - 1) / passes;
+  if (passes == 2 && pl.W > 25) return pl;  // the 2-quad variant is compiled for <= 26 warps (78 registers)
   pl.ok = true;
   return pl;
+}
+
+template <int CPL, int QPW>
+int32_t launch_t(const HeadTileParams& p, const HeadTilePlan& plan, unsigned grid, unsigned block, cudaStream_t st) {
+  static size_t attr_smem = 0;
+  if (plan.smem > attr_smem) {
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)plan.smem));
+    attr_smem = plan.smem;
+  }
+  mp_headtile_kernel<CPL, QPW><<<grid, block, plan.smem, st>>>(p);
+  QAGNN_CHECK_LAUNCH();
+  return QAGNN_OK;
 }
 
 }  // namespace
@@ -320,22 +458,17 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   if (!plan.ok) return QAGNN_ERR_UNSUPPORTED;
   auto I = [&](size_t off) { return (const int32_t*)((const char*)prep_base + off); };
   HeadTileParams p;
-  p.N = s.N; p.Ep = s.N + s.E;
+  p.N = s.N; p.Eps = (s.N + s.E + 3) / 4 * 4;
   p.n = s.n_per_graph; p.G = (int)(s.N / s.n_per_graph); p.H = s.H; p.D = s.D; p.d = s.D / s.H; p.DP = plan.DP;
-  p.C = plan.C; p.S = plan.S; p.W = plan.W;
+  p.C = plan.C; p.S = plan.S; p.W = plan.W; p.ecap = plan.ecap;
   p.rowptr_src = I(L.rowptr_src); p.rowptr_tgt = I(L.rowptr_tgt); p.pk_src = I(L.pk_src); p.pk_tgt = I(L.pk_tgt);
-  p.apos = I(L.csr_tgt_apos); p.perm_src = I(L.perm_src);
+  p.tpos = I(L.csr_src_tpos); p.perm_src = I(L.perm_src);
   p.qkmh = qkmh; p.keh = keh; p.meh = meh; p.score = score; p.alpha = alpha; p.aggr = aggr; p.alpha_out = alpha_out;
   const unsigned grid = (unsigned)(plan.S * s.H), block = (unsigned)(plan.W + 1) * 32;
-  if (plan.cpl == 1) {
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    mp_headtile_kernel<1><<<grid, block, plan.smem, st>>>(p);
-  } else {
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    mp_headtile_kernel<2><<<grid, block, plan.smem, st>>>(p);
-  }
-  QAGNN_CHECK_LAUNCH();
-  return QAGNN_OK;
+  if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1>(p, plan, grid, block, st);
+  return launch_t<2, 2>(p, plan, grid, block, st);
 }
 
 }  // namespace qagnn

@@ -33,7 +33,7 @@ def test_graph_prep_bit_exact(name):
     ref = O.graph_prep_oracle(inp["edge_index"], inp["edge_type"], inp["node_type"], fx["n_ntype"], fx["n_etype"])
     got = {k: prep.array(k).cpu().numpy().astype(np.int64) for k in
            ("src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt", "csr_src_tgt", "csr_src_combo",
-            "csr_tgt_src", "csr_tgt_combo", "csr_tgt_apos")}
+            "csr_tgt_src", "csr_tgt_combo", "csr_tgt_apos", "csr_src_tpos", "pk_src", "pk_tgt")}
     for key in ("src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt"):
         assert np.array_equal(got[key], ref[key]), key
     assert np.array_equal(got["csr_src_tgt"], ref["tgt"][ref["perm_src"]])
@@ -42,6 +42,11 @@ def test_graph_prep_bit_exact(name):
     assert np.array_equal(got["csr_tgt_combo"], ref["combo"][ref["perm_tgt"]])
     inv = np.empty_like(ref["perm_src"]); inv[ref["perm_src"]] = np.arange(len(inv))
     assert np.array_equal(got["csr_tgt_apos"], inv[ref["perm_tgt"]])
+    inv_t = np.empty_like(ref["perm_tgt"]); inv_t[ref["perm_tgt"]] = np.arange(len(inv_t))
+    assert np.array_equal(got["csr_src_tpos"], inv_t[ref["perm_src"]])
+    n = fx["case"]["n"]  # packed (local endpoint << 16 | combo) used by the shared-memory-tiled kernel
+    assert np.array_equal(got["pk_src"], ((ref["tgt"] % n) << 16 | ref["combo"])[ref["perm_src"]])
+    assert np.array_equal(got["pk_tgt"], ((ref["src"] % n) << 16 | ref["combo"])[ref["perm_tgt"]])
     assert torch.equal(prep.edge_index_prime().cpu(), fx["edge_index_prime"])
 
 
