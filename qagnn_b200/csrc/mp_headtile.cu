@@ -83,7 +83,7 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap)
   m.tile0 = (uint32_t)C * DP * 4;
   m.tile_bytes = (uint32_t)n * DP * 4;
   m.rp0 = m.tile0 + 2 * m.tile_bytes;
-  m.rp_bytes = (uint32_t)((n + 1 + 3) / 4 * 4) * 4;
+  m.rp_bytes = (uint32_t)((n + 1 + 3 + 3) / 4 * 4) * 4;  // + alignment slack of the slice start
   m.ia0 = m.rp0 + 2 * m.rp_bytes;
   m.idx_bytes = (uint32_t)ecap * 4;
   m.ib0 = m.ia0 + 2 * m.idx_bytes;
@@ -99,10 +99,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
   const int NCH = p.DP / 4;
   const SmemMap sm = make_smem_map(p.C, p.DP, p.n, p.ecap);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sm.bars);
-  uint64_t* full = bars;        // [2]  1 expect_tx arrival (tile) + 1 arrival (staged indices)
+  uint64_t* full = bars;        // [2]  one expect_tx arrival covering tile + CSR slice bytes
   uint64_t* empty = bars + 2;   // [2]  W consumer arrivals
   uint64_t* tabbar = bars + 4;  // [1]
-  volatile int* meta = reinterpret_cast<volatile int*>(smem_raw + sm.meta);  // [2][2] = {base, staged}
 
   const int h = blockIdx.x % p.H;
   const int slot = blockIdx.x / p.H;
@@ -111,8 +110,8 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 2);
-    mbar_init(&full[1], 2);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     mbar_init(&empty[0], p.W);
     mbar_init(&empty[1], p.W);
     mbar_init(tabbar, 1);
@@ -127,9 +126,11 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
   const size_t hE = (size_t)h * p.Eps;
 
   if (warp == p.W) {
-    // ============ loader warp: TMA ring + CSR slice staging, one graph ahead of the consumers ============
-    if (lane == 0)
-      bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.keh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
+    // ===== loader: ONE thread drives the TMA ring — node tile + CSR slice (row pointers, packed ids, =====
+    // ===== by-target positions / phase-2 weights) of the next graph, all as cp.async.bulk copies     =====
+    if (lane != 0) return;
+    bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.keh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
+    int nb = p.rowptr_src[(size_t)slot * p.n], ne = p.rowptr_src[(size_t)slot * p.n + p.n];  // bounds of graph 0
     for (int t = 0; t < 2 * Gc; ++t) {
       const int b = t & 1;
       const bool ph2 = t >= Gc;
@@ -137,41 +138,36 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
         // phase switch: every consumer has left phase 1 once the last two tiles are released
         mbar_wait(&empty[(Gc - 1) & 1], ((Gc - 1) >> 1) & 1);
         if (Gc >= 2) mbar_wait(&empty[(Gc - 2) & 1], ((Gc - 2) >> 1) & 1);
-        if (lane == 0)
-          bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.meh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
+        bulk_g2s_chunked((char*)(smem_raw + sm.tab), (const char*)(p.meh + (size_t)h * p.C * p.DP), sm.tile0, tabbar);
       }
       if (t >= 2) mbar_wait(&empty[b], ((t >> 1) - 1) & 1);
       const int g = slot + (ph2 ? t - Gc : t) * p.S;
-      if (lane == 0) {
-        const float* src = (ph2 ? Mh : Kh) + (size_t)g * p.n * p.DP;
-        bulk_g2s_chunked((char*)(smem_raw + sm.tile0 + b * sm.tile_bytes), (const char*)src, sm.tile_bytes, &full[b]);
-      }
-      // CSR slice of graph g in the order this phase walks (by source / by target)
-      const int32_t* rowptr = (ph2 ? p.rowptr_tgt : p.rowptr_src) + (size_t)g * p.n;
-      const int seg_beg = rowptr[0], seg_end = rowptr[p.n];
-      const int base = seg_beg & ~3;
-      const int cnt = seg_end - base;
+      const int64_t v0 = (int64_t)g * p.n;
+      const int32_t* rowptr = ph2 ? p.rowptr_tgt : p.rowptr_src;
+      const int base = nb & ~3, cnt = ne - base;
       const bool staged = cnt <= p.ecap;
-      int* rp = reinterpret_cast<int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
-      for (int i = lane; i <= p.n; i += 32) rp[i] = rowptr[i] - base;
-      if (staged) {
-        const int nvec = (cnt + 3) >> 2;
-        int4* ia = reinterpret_cast<int4*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
-        int4* ib = reinterpret_cast<int4*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
-        const int4* ga = reinterpret_cast<const int4*>((ph2 ? p.pk_tgt : p.pk_src) + base);
-        const int4* gb = ph2 ? reinterpret_cast<const int4*>(p.alpha + hE + base)
-                             : reinterpret_cast<const int4*>(p.tpos + base);
-        for (int i = lane; i < nvec; i += 32) {
-          ia[i] = ga[i];
-          ib[i] = gb[i];
-        }
+      const uint32_t idx_bytes = staged ? (uint32_t)((cnt + 3) & ~3) * 4u : 0u;
+      const int64_t rp_base = v0 & ~(int64_t)3;
+      const uint32_t rp_bytes = (uint32_t)(((v0 - rp_base) + p.n + 1 + 3) & ~3) * 4u;
+      mbar_expect_tx(&full[b], sm.tile_bytes + rp_bytes + 2 * idx_bytes);
+      {
+        const char* src = (const char*)((ph2 ? Mh : Kh) + (size_t)v0 * p.DP);
+        char* dst = (char*)(smem_raw + sm.tile0 + b * sm.tile_bytes);
+        for (uint32_t o = 0; o < sm.tile_bytes; o += 32768) bulk_g2s(dst + o, src + o, min(32768u, sm.tile_bytes - o), &full[b]);
       }
-      if (lane == 0) {
-        meta[2 * b] = base;
-        meta[2 * b + 1] = staged ? 1 : 0;
+      bulk_g2s(smem_raw + sm.rp0 + b * sm.rp_bytes, rowptr + rp_base, rp_bytes, &full[b]);
+      if (staged && idx_bytes) {
+        bulk_g2s(smem_raw + sm.ia0 + b * sm.idx_bytes, (ph2 ? p.pk_tgt : p.pk_src) + base, idx_bytes, &full[b]);
+        if (ph2) bulk_g2s(smem_raw + sm.ib0 + b * sm.idx_bytes, p.alpha + hE + base, idx_bytes, &full[b]);
+        else bulk_g2s(smem_raw + sm.ib0 + b * sm.idx_bytes, p.tpos + base, idx_bytes, &full[b]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[b]);
+      if (t + 1 < 2 * Gc) {  // bounds of the next graph, in flight while the consumers work
+        const bool nph2 = t + 1 >= Gc;
+        const int64_t nv0 = (int64_t)(slot + (nph2 ? t + 1 - Gc : t + 1) * p.S) * p.n;
+        const int32_t* nrp = nph2 ? p.rowptr_tgt : p.rowptr_src;
+        nb = nrp[nv0];
+        ne = nrp[nv0 + p.n];
+      }
     }
     return;
   }
@@ -216,19 +212,19 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     }
     mbar_wait(&full[b], (t >> 1) & 1);
     const float4* kt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
-    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
+    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
     const int* ib = reinterpret_cast<const int*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
-    const int base = meta[2 * b];
-    const bool staged = meta[2 * b + 1] != 0;
+    const int base = rp[0] & ~3;
+    const bool staged = rp[p.n] - base <= p.ecap;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
       const int quad = warp + u * p.W;
       if (quad >= nquads) break;
       const int vl = quad * 4 + qi;
       const bool nvalid = vl < p.n;
-      const int begr = rp[nvalid ? vl : 0];
-      const int deg = nvalid ? rp[vl + 1] - begr : 0;
+      const int begr = rp[nvalid ? vl : 0] - base;
+      const int deg = nvalid ? rp[vl + 1] - base - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
       float skeep = -INFINITY;  // lane j keeps the logit of edge j (j < 8)
@@ -291,6 +287,7 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
       }
     }
     __threadfence_block();
+    asm volatile("fence.proxy.async;" ::: "memory");  // a'[e] is read back by cp.async.bulk (async proxy) in phase 2
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
   }
@@ -302,19 +299,19 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     const int g = slot + (t - Gc) * p.S;
     mbar_wait(&full[b], (t >> 1) & 1);
     const float4* mt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
-    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes);
+    const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
     const float* ib = reinterpret_cast<const float*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
-    const int base = meta[2 * b];
-    const bool staged = meta[2 * b + 1] != 0;
+    const int base = rp[0] & ~3;
+    const bool staged = rp[p.n] - base <= p.ecap;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
       const int quad = warp + u * p.W;
       if (quad >= nquads) break;
       const int vl = quad * 4 + qi;
       const bool nvalid = vl < p.n;
-      const int begr = rp[nvalid ? vl : 0];
-      const int deg = nvalid ? rp[vl + 1] - begr : 0;
+      const int begr = rp[nvalid ? vl : 0] - base;
+      const int deg = nvalid ? rp[vl + 1] - base - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
       float2 acc[CPL][2];
