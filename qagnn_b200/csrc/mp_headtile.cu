@@ -180,7 +180,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     cvalid[k] = (l8 + 8 * k) < NCH;
-    chunk[k] = cvalid[k] ? l8 + 8 * k : 0;  // idle lanes re-read chunk 0 (finite data) against q = 0
+    // idle lanes re-read their own first chunk against q = 0: finite data, and (unlike chunk 0) bytes
+    // 16*l8.. do not share banks with chunks 8.. that the active lanes of the quarter-warp read
+    chunk[k] = cvalid[k] ? l8 + 8 * k : l8;
   }
   const float4* tab = reinterpret_cast<const float4*>(smem_raw + sm.tab);
 
@@ -265,25 +267,37 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
         }
       }
       // softmax over this node's out-edges, lane-parallel (lane j <-> edge j, j + 8, ...)
-      if (maxdeg > 8) __syncwarp();
+      const bool hub = maxdeg > 8;  // warp-uniform; logits beyond the 8th edge live in the L2 scratch
+      if (hub) __syncwarp();
       float m = (l8 < deg) ? skeep : -INFINITY;
-      for (int j = 8 + l8; j < deg; j += 8) m = fmaxf(m, p.score[hE + base + begr + j]);
+      if (hub)
+        for (int j = 8 + l8; j < deg; j += 8) m = fmaxf(m, p.score[hE + base + begr + j]);
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      float ex0 = (l8 < deg) ? expf(skeep - m) : 0.f;
+      const float ex0 = (l8 < deg) ? __expf(skeep - m) : 0.f;
       float ssum = ex0;
-      for (int j = 8 + l8; j < deg; j += 8) ssum += expf(p.score[hE + base + begr + j] - m);
+      if (hub)
+        for (int j = 8 + l8; j < deg; j += 8) ssum += __expf(p.score[hE + base + begr + j] - m);
       ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
       ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
       ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
-      const float denom = ssum + 1e-16f;  // torch_geometric.utils.softmax
-      const float degf = (float)deg;      // out-degree of the source, self loop included (:476-481)
-      for (int j = l8; j < deg; j += 8) {
-        const float a = (j < 8 ? ex0 : expf(p.score[hE + base + begr + j] - m)) / denom;
-        const int tp = staged ? ib[begr + j] : p.tpos[base + begr + j];
+      // a = ex / (sum + 1e-16) (torch_geometric.utils.softmax), then * out-degree of the source (:476-481)
+      const float rden = __fdividef(1.f, ssum + 1e-16f);
+      const float degf = (float)deg;
+      if (l8 < deg) {
+        const float a = ex0 * rden;
+        const int tp = staged ? ib[begr + l8] : p.tpos[base + begr + l8];
         p.alpha[hE + tp] = a * degf;  // stored in by-target order for phase 2
-        if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[base + begr + j] * p.H + h] = a;
+        if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[base + begr + l8] * p.H + h] = a;
+      }
+      if (hub) {
+        for (int j = 8 + l8; j < deg; j += 8) {
+          const float a = __expf(p.score[hE + base + begr + j] - m) * rden;
+          const int tp = staged ? ib[begr + j] : p.tpos[base + begr + j];
+          p.alpha[hE + tp] = a * degf;
+          if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[base + begr + j] * p.H + h] = a;
+        }
       }
     }
     __threadfence_block();
