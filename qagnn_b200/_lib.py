@@ -71,6 +71,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
+    if os.path.exists(LIB_PATH) and not _build.is_current():
+        # sources changed since the library was built: rebuild when a compiler is around, never run stale code
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f"{LIB_PATH} is older than qagnn_b200/csrc and could not be rebuilt: {e}") from e
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: the qagnn_b200 CUDA library has not been built. Run "

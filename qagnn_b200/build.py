@@ -39,6 +39,12 @@ def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
 
 
+def is_current():
+    """True when the in-tree library was built from the current sources."""
+    stamp_file = lib_path() + ".stamp"
+    return os.path.exists(lib_path()) and os.path.exists(stamp_file) and open(stamp_file).read() == _stamp()
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library.  Returns its path."""
     os.makedirs(LIBDIR, exist_ok=True)
