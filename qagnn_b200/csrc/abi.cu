@@ -63,6 +63,13 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   W.xb = take(N * D);
   W.extra = take(N * D);
   W.sinb = take(N * (D / 2));
+  const size_t half = N * D / 2 + 8;  // one bf16 plane [N, D], in floats
+  W.hp_hi = take(half); W.hp_lo = take(half);
+  W.ep_hi = take(half); W.ep_lo = take(half);
+  W.xp_hi[0] = take(half); W.xp_lo[0] = take(half);
+  W.xp_hi[1] = take(half); W.xp_lo[1] = take(half);
+  W.ap_hi = take(half); W.ap_lo = take(half);
+  W.mp_hi = take(half); W.mp_lo = take(half);
   const size_t Eps = (Ep + 3) / 4 * 4;  // per-head stride of the tiled path
   W.score = take(Eps * H);
   W.alpha = take(Eps * H);
@@ -137,6 +144,59 @@ int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
     ProfScope ps(QAGNN_PROF_NODE_MLP, st);
     QAGNN_RETURN_IF(sgemm_tn(aggr, D, D, nullptr, 0, 0, lb + L.w1, D, lb + L.b1, ws + W.hmid, D, s.N, D, ACT_RELU, st));
     QAGNN_RETURN_IF(sgemm_tn(ws + W.hmid, D, D, nullptr, 0, 0, lb + L.w2, D, lb + L.b2, out, D, s.N, D, final_act, st));
+  }
+  return QAGNN_OK;
+}
+
+// Dense-path selection: tcgen05 split-bf16 GEMMs when the driver exposes TMA descriptors and the row strides
+// meet TMA's 16-byte rule (D % 8 == 0); else the exact-fp32 FFMA GEMM.  QAGNN_GEMM=ffma forces the latter.
+bool use_tc(const qagnn_shape& s) { return gemm_tc_available() && s.D % 8 == 0; }
+
+struct Planes {
+  const void* hi;
+  const void* lo;
+};
+
+// one GATConvE layer on split-bf16 planes.  x / extra are [N, D] plane pairs; the layer output goes to any of
+// out_f32 (fp32 [N, D]) and out_planes.
+int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, int layer, Planes x, Planes extra,
+                         const void* prep, const qagnn_prep_layout& pl, const float* folded, float* out_f32,
+                         void* out_hi, void* out_lo, float* alpha_out, float* aggr_out, float* ws, Act final_act,
+                         bool tiled, cudaStream_t st) {
+  const int D = s.D;
+  const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
+  float* qkm = ws + W.qkm;
+  float* aggr = aggr_out ? aggr_out : ws + W.aggr;
+  {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
+    ProfScope ps(QAGNN_PROF_PROJECTION, st);
+    TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D}, Wp{lb + L.wp_hi, lb + L.wp_lo, 2 * D, 2 * D};
+    TcOutput o{};
+    if (tiled) { o.hm_buf = qkm; o.hm = HeadMajorOut{1, D, D / s.H, head_dim_padded(D / s.H), s.H}; }
+    else { o.f32 = qkm; o.ldc = 3 * D; }
+    QAGNN_RETURN_IF(gemm_tc(A1, A2, Wp, lb + L.bp, s.N, 3 * D, ACT_NONE, o, st));
+  }
+  {  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
+    ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
+    if (tiled) {
+      QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
+                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, st));
+    } else {
+      QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
+                                             ws + W.alpha, aggr, alpha_out, st));
+    }
+  }
+  {  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
+    ProfScope ps(QAGNN_PROF_NODE_MLP, st);
+    QAGNN_RETURN_IF(split_bf16(aggr, D, s.N, D, ws + W.ap_hi, ws + W.ap_lo, D, st));
+    TcOperand A{ws + W.ap_hi, ws + W.ap_lo, D, D}, none{nullptr, nullptr, 0, 0};
+    TcOperand W1{lb + L.w1_hi, lb + L.w1_lo, D, D}, W2{lb + L.w2_hi, lb + L.w2_lo, D, D};
+    TcOutput o1{};
+    o1.hi = ws + W.mp_hi; o1.lo = ws + W.mp_lo; o1.ldp = D;
+    QAGNN_RETURN_IF(gemm_tc(A, none, W1, lb + L.b1, s.N, D, ACT_RELU, o1, st));
+    TcOperand Hm{ws + W.mp_hi, ws + W.mp_lo, D, D};
+    TcOutput o2{};
+    o2.f32 = out_f32; o2.ldc = D; o2.hi = out_hi; o2.lo = out_lo; o2.ldp = D;
+    QAGNN_RETURN_IF(gemm_tc(Hm, none, W2, lb + L.b2, s.N, D, final_act, o2, st));
   }
   return QAGNN_OK;
 }
@@ -216,9 +276,18 @@ extern "C" int32_t qagnn_gatconve_forward(const qagnn_shape* shape, int32_t laye
   qagnn_prep_layout pl;
   QAGNN_RETURN_IF(qagnn_graph_prep_layout(shape->N, shape->E, &pl));
   const bool tiled = use_headtile(*shape);
-  if (tiled) QAGNN_RETURN_IF(zero_head_pads(*shape, (float*)workspace + W.qkm, (cudaStream_t)stream));
-  return layer_forward(*shape, L, W, layer, x, extra, prep, pl, (const float*)folded, out, alpha_out, aggr_out,
-                       (float*)workspace, ACT_NONE, tiled, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  if (tiled) QAGNN_RETURN_IF(zero_head_pads(*shape, ws + W.qkm, st));
+  if (use_tc(*shape)) {
+    const int D = shape->D;
+    QAGNN_RETURN_IF(split_bf16(x, D, shape->N, D, ws + W.xp_hi[0], ws + W.xp_lo[0], D, st));
+    QAGNN_RETURN_IF(split_bf16(extra, D, shape->N, D, ws + W.ep_hi, ws + W.ep_lo, D, st));
+    return layer_forward_tc(*shape, L, W, layer, Planes{ws + W.xp_hi[0], ws + W.xp_lo[0]}, Planes{ws + W.ep_hi, ws + W.ep_lo},
+                            prep, pl, (const float*)folded, out, nullptr, nullptr, alpha_out, aggr_out, ws, ACT_NONE, tiled, st);
+  }
+  return layer_forward(*shape, L, W, layer, x, extra, prep, pl, (const float*)folded, out, alpha_out, aggr_out, ws,
+                       ACT_NONE, tiled, st);
 }
 
 extern "C" int32_t qagnn_node_feature_extra(const qagnn_shape* shape, const int64_t* node_type, const float* node_score,
@@ -252,6 +321,31 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   const bool tiled = use_headtile(s);
   if (tiled) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
   const size_t ND = (size_t)s.N * s.D;
+  if (use_tc(s)) {
+    const int D = s.D;
+    {
+      ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
+      QAGNN_RETURN_IF(split_bf16(extra, D, s.N, D, ws + W.ep_hi, ws + W.ep_lo, D, st));
+      QAGNN_RETURN_IF(split_bf16(H_in, D, s.N, D, ws + W.hp_hi, ws + W.hp_lo, D, st));
+    }
+    Planes xin{ws + W.hp_hi, ws + W.hp_lo};
+    const Planes ep{ws + W.ep_hi, ws + W.ep_lo};
+    for (int l = 0; l < s.k; ++l) {  // mp_helper, :45-50 (dropout is the identity in eval)
+      float* xo32 = x_layers_out ? x_layers_out + (size_t)l * ND : nullptr;
+      void* ohi = ws + W.xp_hi[l & 1];
+      void* olo = ws + W.xp_lo[l & 1];
+      QAGNN_RETURN_IF(layer_forward_tc(s, L, W, l, xin, ep, prep, pl, f, xo32, ohi, olo, nullptr, nullptr, ws, ACT_GELU,
+                                       tiled, st));
+      xin = Planes{ohi, olo};
+    }
+    // output = GELU(Vh(H) + Vx(X))                                           (:92)
+    ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
+    TcOperand A1{ws + W.hp_hi, ws + W.hp_lo, D, D}, A2{xin.hi, xin.lo, D, D}, Wv{f + L.vcat_hi, f + L.vcat_lo, 2 * D, 2 * D};
+    TcOutput o{};
+    o.f32 = out; o.ldc = D;
+    if (s.k == 0) { A2 = A1; }
+    return gemm_tc(A1, A2, Wv, f + L.vbias, s.N, D, ACT_GELU, o, st);
+  }
   const float* x = H_in;
   for (int l = 0; l < s.k; ++l) {  // mp_helper, :45-50 (dropout is the identity in eval)
     float* xo = x_layers_out ? x_layers_out + (size_t)l * ND : ws + ((l & 1) ? W.xb : W.xa);

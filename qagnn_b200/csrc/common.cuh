@@ -69,6 +69,11 @@ struct FoldLayout {
   size_t b2;         // [D]
   size_t keh;        // [H, C, DP] head-major zero-padded copy of ke (DP = d rounded up to 4)
   size_t meh;        // [H, C, DP]
+  // split-bf16 planes of the dense weights (tensor-core path); sizes in floats = elements / 2 per plane
+  size_t wp_hi, wp_lo;   // [3D, 2D]
+  size_t w1_hi, w1_lo;   // [D, D]
+  size_t w2_hi, w2_lo;   // [D, D]
+  size_t vcat_hi, vcat_lo;  // [D, 2D]  (global, not per layer)
   size_t total;      // floats
 };
 FoldLayout make_fold_layout(const qagnn_shape& s);
@@ -81,6 +86,12 @@ struct WorkLayout {
   size_t xa, xb;  // [N, D] ping-pong layer activations
   size_t extra;   // [N, D]
   size_t sinb;    // [N, D/2]
+  // split-bf16 planes [N, D] x {hi, lo} of the GEMM A operands (tensor-core path)
+  size_t hp_hi, hp_lo;          // H_in
+  size_t ep_hi, ep_lo;          // node_feature_extra
+  size_t xp_hi[2], xp_lo[2];    // layer activations, ping-pong
+  size_t ap_hi, ap_lo;          // aggr
+  size_t mp_hi, mp_lo;          // mlp hidden
   size_t score;   // [E', H]  raw logits / exp scratch (by-source order)
   size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order)
   size_t total;   // floats
@@ -102,6 +113,25 @@ struct HeadMajorOut {
 int32_t sgemm_tn(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* W, int ldw,
                  const float* bias, float* C, int ldc, int64_t M, int N, Act act, cudaStream_t st,
                  HeadMajorOut hm = HeadMajorOut{0, 0, 0, 0, 0});
+
+// ---- tensor-core GEMM on split-bf16 planes (gemm_tc.cu) ---------------------------------------------
+// An operand is a pair of bf16 planes [rows, K] (ld elements each): value = hi + lo.
+struct TcOperand {
+  const void* hi;
+  const void* lo;
+  int ld, K;
+};
+// Any subset of: fp32 row-major C, fp32 head-major padded (projection for the tiled MP), split-bf16 planes.
+struct TcOutput {
+  float* f32; int ldc;
+  float* hm_buf; HeadMajorOut hm;
+  void* hi; void* lo; int ldp;
+};
+bool gemm_tc_available();
+bool gemm_tc_shape_ok(int K1, int K2, int lda1, int lda2, int ldw, int N);
+int32_t split_bf16(const float* a, int lda, long long M, int K, void* hi, void* lo, int ldp, cudaStream_t st);
+int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, const float* bias, long long M, int N,
+                Act act, const TcOutput& out, cudaStream_t st);
 
 // ---- shared-memory-tiled message passing (mp_headtile.cu) ----------------------------------------------
 inline int head_dim_padded(int d) { return (d + 3) / 4 * 4; }

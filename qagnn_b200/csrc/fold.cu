@@ -28,6 +28,8 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   L.bs = take(Dh);
   L.vcat = take(D * 2 * D);
   L.vbias = take(D);
+  L.vcat_hi = take(D * 2 * D / 2);
+  L.vcat_lo = take(D * 2 * D / 2);
   L.layer0 = o;
   size_t lo = 0;
   auto ltake = [&](size_t n) { size_t r = lo; lo += align_up(n * 4) / 4; return r; };
@@ -42,6 +44,12 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   const size_t DP = (size_t)head_dim_padded(s.D / s.H);
   L.keh = ltake((size_t)s.H * C * DP);
   L.meh = ltake((size_t)s.H * C * DP);
+  L.wp_hi = ltake(3 * D * 2 * D / 2);
+  L.wp_lo = ltake(3 * D * 2 * D / 2);
+  L.w1_hi = ltake(D * D / 2);
+  L.w1_lo = ltake(D * D / 2);
+  L.w2_hi = ltake(D * D / 2);
+  L.w2_lo = ltake(D * D / 2);
   L.layer_stride = lo;
   L.total = o + lo * (size_t)(s.k > 0 ? s.k : 0);
   return L;
@@ -203,6 +211,11 @@ extern "C" int32_t qagnn_fold_weights(const qagnn_shape* shape, const qagnn_edge
     fold_head_major_kernel<<<(unsigned)((nhm + 255) / 256), 256, 0, st>>>(C, D, shape->H, DP, lb + L.ke, lb + L.me,
                                                                           lb + L.keh, lb + L.meh);
     QAGNN_CHECK_LAUNCH();
+    if (D % 2 == 0) {  // split-bf16 planes of the dense weights for the tensor-core GEMMs
+      QAGNN_RETURN_IF(split_bf16(lb + L.wp, 2 * D, 3 * D, 2 * D, lb + L.wp_hi, lb + L.wp_lo, 2 * D, st));
+      QAGNN_RETURN_IF(split_bf16(lb + L.w1, D, D, D, lb + L.w1_hi, lb + L.w1_lo, D, st));
+      QAGNN_RETURN_IF(split_bf16(lb + L.w2, D, D, D, lb + L.w2_hi, lb + L.w2_lo, D, st));
+    }
   }
   if (mp) {
     const int Dh = D / 2;
@@ -211,6 +224,7 @@ extern "C" int32_t qagnn_fold_weights(const qagnn_shape* shape, const qagnn_edge
         D, shape->T, mp->emb_node_type_w, mp->emb_node_type_b, mp->emb_score_w, mp->emb_score_b, mp->vh_w, mp->vh_b,
         mp->vx_w, mp->vx_b, mp->score_basis, f + L.type_tab, f + L.basis, f + L.ws, f + L.bs, f + L.vcat, f + L.vbias);
     QAGNN_CHECK_LAUNCH();
+    if (D % 2 == 0) QAGNN_RETURN_IF(split_bf16(f + L.vcat, 2 * D, D, 2 * D, f + L.vcat_hi, f + L.vcat_lo, 2 * D, st));
   }
   return QAGNN_OK;
 }

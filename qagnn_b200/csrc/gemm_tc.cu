@@ -1,0 +1,391 @@
+// Tensor-core GEMM for the dense node-level linears of the hot path (the W_q/W_k/W_m projection, the
+// node MLP, Vh/Vx — modeling/modeling_qagnn.py:464-466 node part, :443/:408, :92):
+//
+//     C[M,N] = act( [A1 | A2] @ W^T + bias )          fp32 in, fp32 accumulate, fp32-faithful out
+//
+// Blackwell-native: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands
+// staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring, one elected
+// thread issuing the MMAs, tcgen05.ld epilogue.  Warp roles per CTA (192 threads):
+//     warp 0  TMA producer      warp 1  TMEM alloc + MMA issuer      warps 2-5  epilogue
+//
+// Precision: the reference runs these linears in fp32 and parity is 1e-4, which single-pass bf16
+// (2^-9) or tf32 (2^-11) cannot hold.  Operands are therefore stored as SPLIT-BF16 planes
+//     a = a_hi + a_lo,  a_hi = bf16(a), a_lo = bf16(a - a_hi)        (16 mantissa bits)
+// and each k-step issues three MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 accumulator: the
+// dropped terms are O(2^-17) relative, ~50x below the parity bar, at 3 tensor passes instead of
+// the ~30x slower FFMA path (sgemm.cu, kept as the exact-fp32 fallback).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace qagnn {
+
+namespace {
+
+constexpr int BM = 128;     // rows per CTA tile = UMMA M
+constexpr int BK = 64;      // bf16 per k-block = 128 bytes = one swizzle span
+constexpr int kThreads = 192;
+
+struct alignas(64) TcParams {
+  CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo;
+  int nseg, kseg[2];
+  int umma_n, n_step, N, stages;
+  long long M;
+  const float* bias;
+  int act;
+  float* c_f32;
+  int ldc;
+  float* c_hm;
+  HeadMajorOut hm;
+  __nv_bfloat16 *c_hi, *c_lo;
+  int ldp;
+  unsigned tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO=1 | SBO=64 | version=1 | layout=SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = BM * BK * 2;              // one A plane tile: 16 KB
+  const uint32_t w_bytes = (uint32_t)p.umma_n * BK * 2;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  unsigned char* ctrl = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);       // [stages]
+  uint64_t* empty = full + p.stages;                        // [stages]
+  uint64_t* accbar = empty + p.stages;                      // [1] accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accbar + 1);
+
+  const int n0 = blockIdx.x * p.n_step;
+  const long long m0 = (long long)blockIdx.y * BM;
+
+  // k-blocks across the (up to two) A segments
+  int nkb_seg[2];
+  nkb_seg[0] = (p.kseg[0] + BK - 1) / BK;
+  nkb_seg[1] = p.nseg > 1 ? (p.kseg[1] + BK - 1) / BK : 0;
+  const int nkb = nkb_seg[0] + nkb_seg[1];
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        if (kb >= p.stages) mbar_wait(&empty[s], ((kb / p.stages) - 1) & 1);
+        const int seg = kb < nkb_seg[0] ? 0 : 1;
+        const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
+        const int k_glob = (seg == 0 ? 0 : p.kseg[0]) + k_in_seg;
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], stage_bytes);
+        tma_load_2d(st, &p.a_hi[seg], k_in_seg, (int)m0, &full[s]);
+        tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, (int)m0, &full[s]);
+        tma_load_2d(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
+        tma_load_2d(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(&full[s], (kb / p.stages) & 1);
+        tc_fence_after();
+        const int seg = kb < nkb_seg[0] ? 0 : 1;
+        const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
+        const int krem = p.kseg[seg] - k_in_seg;
+        const int nsteps = krem >= BK ? BK / 16 : (krem + 15) / 16;  // skip k-steps that are pure zero fill
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        for (int k = 0; k < nsteps; ++k) {
+          const uint64_t da_hi = umma_desc(sa + k * 32), da_lo = umma_desc(sa + a_bytes + k * 32);
+          const uint64_t dw_hi = umma_desc(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc(sa + 2 * a_bytes + w_bytes + k * 32);
+          umma_bf16(tmem_base, da_hi, dw_hi, idesc, (kb | k) != 0);
+          umma_bf16(tmem_base, da_hi, dw_lo, idesc, 1u);
+          umma_bf16(tmem_base, da_lo, dw_hi, idesc, 1u);
+        }
+        umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+      }
+      umma_commit(accbar);
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5) =====================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const long long row = m0 + quad * 32 + lane;
+    const int n_end = min(n0 + p.n_step, p.N);
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.umma_n && n0 + c0 < n_end; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (row >= p.M) continue;
+      const int col0 = n0 + c0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i];
+        if (p.bias != nullptr && col0 + i < n_end) x += p.bias[col0 + i];
+        if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+        if (p.act == ACT_GELU) x = gelu_tanh(x);
+        v[i] = x;
+      }
+      if (p.c_f32 != nullptr) {
+        float* dst = p.c_f32 + row * p.ldc + col0;
+        if (col0 + 16 <= n_end && (p.ldc & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col0 + i < n_end) dst[i] = v[i];
+        }
+      }
+      if (p.c_hm != nullptr) {
+        // logical column -> (which, head, j) of the head-major padded layout [3][H][M][DP], advanced incrementally.
+        // D and d even => a head starts on an even column, so (even, odd) column pairs never straddle heads.
+        const int D = p.hm.D, d = p.hm.d;
+        int which = col0 / D, hh = (col0 % D) / d, jj = (col0 % D) % d;
+        if ((d & 1) == 0 && (D & 1) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float* dst = p.c_hm + ((size_t)(which * p.hm.H + hh) * p.M + row) * p.hm.DP + jj;
+            if (col0 + i + 1 < n_end) *reinterpret_cast<float2*>(dst) = make_float2(v[i], v[i + 1]);
+            else if (col0 + i < n_end) *dst = v[i];
+            jj += 2;
+            if (jj >= d) { jj = 0; if (++hh == p.hm.H) { hh = 0; ++which; } }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (col0 + i < n_end) p.c_hm[((size_t)(which * p.hm.H + hh) * p.M + row) * p.hm.DP + jj] = v[i];
+            if (++jj == d) { jj = 0; if (++hh == p.hm.H) { hh = 0; ++which; } }
+          }
+        }
+      }
+      if (p.c_hi != nullptr) {
+        __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          hi[i] = __float2bfloat16_rn(v[i]);
+          lo[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hi[i]));
+        }
+        __nv_bfloat16* dh = p.c_hi + row * p.ldp + col0;
+        __nv_bfloat16* dl = p.c_lo + row * p.ldp + col0;
+        if (col0 + 16 <= n_end && (p.ldp & 7) == 0) {
+          *reinterpret_cast<uint4*>(dh) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(dh + 8) = *reinterpret_cast<const uint4*>(hi + 8);
+          *reinterpret_cast<uint4*>(dl) = *reinterpret_cast<const uint4*>(lo);
+          *reinterpret_cast<uint4*>(dl + 8) = *reinterpret_cast<const uint4*>(lo + 8);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col0 + i < n_end) { dh[i] = hi[i]; dl[i] = lo[i]; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ a, int lda, long long M, int K, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int ldp) {
+  const long long total = M * (long long)(K / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (K / 2);
+    const int c = (int)(i % (K / 2)) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(a + r * lda + c);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    __nv_bfloat162 hh, ll;
+    hh.x = h0; hh.y = h1;
+    ll.x = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+    ll.y = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+    *reinterpret_cast<__nv_bfloat162*>(hi + r * ldp + c) = hh;
+    *reinterpret_cast<__nv_bfloat162*>(lo + r * ldp + c) = ll;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// [rows, K] bf16 row-major (ld elements) -> 2-D tensor map with a {64, box_rows} box, 128-byte swizzle
+bool make_map(CUtensorMap* m, const void* base, long long rows, int K, int ld, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool gemm_tc_available() {
+  static const bool forced_off = [] {
+    const char* e = getenv("QAGNN_GEMM");
+    return e && strcmp(e, "ffma") == 0;
+  }();
+  return !forced_off && encode_fn() != nullptr;
+}
+
+bool gemm_tc_shape_ok(int K1, int K2, int lda1, int lda2, int ldw, int N) {
+  return K1 > 0 && K1 % 8 == 0 && (K2 == 0 || K2 % 8 == 0) && lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldw % 8 == 0 && N >= 8;
+}
+
+int32_t split_bf16(const float* a, int lda, long long M, int K, void* hi, void* lo, int ldp, cudaStream_t st) {
+  if (M <= 0 || K <= 0) return QAGNN_OK;
+  if (K % 2 != 0 || lda % 2 != 0) return QAGNN_ERR_UNSUPPORTED;
+  long long g = (M * (K / 2) + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  split_bf16_kernel<<<(unsigned)g, 256, 0, st>>>(a, lda, M, K, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp);
+  QAGNN_CHECK_LAUNCH();
+  return QAGNN_OK;
+}
+
+int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, const float* bias, long long M, int N, Act act,
+                const TcOutput& out, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return QAGNN_OK;
+  if (!gemm_tc_available()) return QAGNN_ERR_UNSUPPORTED;
+  const int K1 = A1.K, K2 = A2.hi ? A2.K : 0;
+  if (!gemm_tc_shape_ok(K1, K2, A1.ld, A2.ld, W.ld, N)) return QAGNN_ERR_UNSUPPORTED;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int n_tiles = (N + 255) / 256;
+  p.n_step = (N + n_tiles - 1) / n_tiles;
+  p.n_step = (p.n_step + 7) / 8 * 8;
+  p.umma_n = (p.n_step + 15) / 16 * 16;
+  p.N = N;
+  p.M = M;
+  p.nseg = K2 > 0 ? 2 : 1;
+  p.kseg[0] = K1;
+  p.kseg[1] = K2;
+  p.tmem_cols = p.umma_n <= 32 ? 32 : p.umma_n <= 64 ? 64 : p.umma_n <= 128 ? 128 : 256;
+  const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM);
+  if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM);
+  ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n);
+  if (!ok) return QAGNN_ERR_CUDA;
+  p.bias = bias;
+  p.act = (int)act;
+  p.c_f32 = out.f32;
+  p.ldc = out.ldc;
+  p.c_hm = out.hm_buf;
+  p.hm = out.hm;
+  p.c_hi = (__nv_bfloat16*)out.hi;
+  p.c_lo = (__nv_bfloat16*)out.lo;
+  p.ldp = out.ldp;
+  static size_t attr = 0;
+  if (smem_bytes > attr) {
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    attr = smem_bytes;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)((M + BM - 1) / BM));
+  gemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
+  QAGNN_CHECK_LAUNCH();
+  return QAGNN_OK;
+}
+
+}  // namespace qagnn
