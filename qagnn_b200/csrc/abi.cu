@@ -169,11 +169,20 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
   float* aggr = aggr_out ? aggr_out : ws + W.aggr;
   {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
     ProfScope ps(QAGNN_PROF_PROJECTION, st);
-    TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D}, Wp{lb + L.wp_hi, lb + L.wp_lo, 2 * D, 2 * D};
+    TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D};
     TcOutput o{};
-    if (tiled) { o.hm_buf = qkm; o.hm = HeadMajorOut{1, D, D / s.H, head_dim_padded(D / s.H), s.H}; }
-    else { o.f32 = qkm; o.ldc = 3 * D; }
-    QAGNN_RETURN_IF(gemm_tc(A1, A2, Wp, lb + L.bp, s.N, 3 * D, ACT_NONE, o, st));
+    if (tiled) {  // per-head padded weight rows -> the GEMM writes [3][H][N][DP] (pads = exact zeros) itself
+      const int DP = head_dim_padded(D / s.H);
+      TcOperand Wp{lb + L.wph_hi, lb + L.wph_lo, 2 * D, 2 * D};
+      o.hm_buf = qkm;
+      o.hm = HeadMajorOut{1, D, D / s.H, DP, s.H};
+      QAGNN_RETURN_IF(gemm_tc(A1, A2, Wp, lb + L.bph, s.N, 3 * s.H * DP, ACT_NONE, o, st));
+    } else {
+      TcOperand Wp{lb + L.wp_hi, lb + L.wp_lo, 2 * D, 2 * D};
+      o.f32 = qkm;
+      o.ldc = 3 * D;
+      QAGNN_RETURN_IF(gemm_tc(A1, A2, Wp, lb + L.bp, s.N, 3 * D, ACT_NONE, o, st));
+    }
   }
   {  // logits -> per-source softmax -> out-degree rescale -> per-target sum   (:442, :469-484)
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
@@ -278,7 +287,7 @@ extern "C" int32_t qagnn_gatconve_forward(const qagnn_shape* shape, int32_t laye
   const bool tiled = use_headtile(*shape);
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
-  if (tiled) QAGNN_RETURN_IF(zero_head_pads(*shape, ws + W.qkm, st));
+  if (tiled && !use_tc(*shape)) QAGNN_RETURN_IF(zero_head_pads(*shape, ws + W.qkm, st));
   if (use_tc(*shape)) {
     const int D = shape->D;
     QAGNN_RETURN_IF(split_bf16(x, D, shape->N, D, ws + W.xp_hi[0], ws + W.xp_lo[0], D, st));
@@ -319,7 +328,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   float* extra = ws + W.extra;
   QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, extra, ws, st));
   const bool tiled = use_headtile(s);
-  if (tiled) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
+  if (tiled && !use_tc(s)) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
   const size_t ND = (size_t)s.N * s.D;
   if (use_tc(s)) {
     const int D = s.D;

@@ -71,6 +71,8 @@ struct FoldLayout {
   size_t meh;        // [H, C, DP]
   // split-bf16 planes of the dense weights (tensor-core path); sizes in floats = elements / 2 per plane
   size_t wp_hi, wp_lo;   // [3D, 2D]
+  size_t wph, bph;       // fp32 [3*H*DP, 2D] / [3*H*DP]: projection rows regrouped per head and zero-padded to DP
+  size_t wph_hi, wph_lo; // its planes — the GEMM then emits the tiled path's [3][H][N][DP] layout directly
   size_t w1_hi, w1_lo;   // [D, D]
   size_t w2_hi, w2_lo;   // [D, D]
   size_t vcat_hi, vcat_lo;  // [D, 2D]  (global, not per layer)

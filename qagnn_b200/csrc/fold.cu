@@ -44,6 +44,10 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   const size_t DP = (size_t)head_dim_padded(s.D / s.H);
   L.keh = ltake((size_t)s.H * C * DP);
   L.meh = ltake((size_t)s.H * C * DP);
+  L.wph = ltake(3 * (size_t)s.H * DP * 2 * D);
+  L.bph = ltake(3 * (size_t)s.H * DP);
+  L.wph_hi = ltake(3 * (size_t)s.H * DP * 2 * D / 2);
+  L.wph_lo = ltake(3 * (size_t)s.H * DP * 2 * D / 2);
   L.wp_hi = ltake(3 * D * 2 * D / 2);
   L.wp_lo = ltake(3 * D * 2 * D / 2);
   L.w1_hi = ltake(D * D / 2);
@@ -142,6 +146,22 @@ __global__ void fold_mp_kernel(int D, int T, const float* __restrict__ tw, const
   }
 }
 
+// projection weight [3D, 2D] (+bias [3D]) -> rows regrouped as [3][H][DP] with zero rows in the pads
+__global__ void fold_pad_projection_kernel(int D, int H, int DP, const float* __restrict__ wp, const float* __restrict__ bp,
+                                           float* __restrict__ wph, float* __restrict__ bph) {
+  const int d = D / H, K = 2 * D;
+  const int64_t rows = (int64_t)3 * H * DP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * (K + 1); i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (K + 1);
+    const int c = (int)(i % (K + 1));
+    const int j = (int)(r % DP), slab = (int)(r / DP);  // slab = which*H + h
+    const int src_row = (slab / H) * D + (slab % H) * d + j;
+    const bool ok = j < d;
+    if (c < K) wph[r * K + c] = ok ? wp[(size_t)src_row * K + c] : 0.f;
+    else bph[r] = ok ? bp[src_row] : 0.f;
+  }
+}
+
 // [C, D] -> head-major zero-padded [H, C, DP]
 __global__ void fold_head_major_kernel(int C, int D, int H, int DP, const float* __restrict__ ke,
                                        const float* __restrict__ me, float* __restrict__ keh,
@@ -213,6 +233,11 @@ extern "C" int32_t qagnn_fold_weights(const qagnn_shape* shape, const qagnn_edge
     QAGNN_CHECK_LAUNCH();
     if (D % 2 == 0) {  // split-bf16 planes of the dense weights for the tensor-core GEMMs
       QAGNN_RETURN_IF(split_bf16(lb + L.wp, 2 * D, 3 * D, 2 * D, lb + L.wp_hi, lb + L.wp_lo, 2 * D, st));
+      const int64_t rows = (int64_t)3 * shape->H * DP;
+      fold_pad_projection_kernel<<<(unsigned)((rows * (2 * D + 1) + 255) / 256), 256, 0, st>>>(D, shape->H, DP, lb + L.wp, lb + L.bp,
+                                                                                          lb + L.wph, lb + L.bph);
+      QAGNN_CHECK_LAUNCH();
+      QAGNN_RETURN_IF(split_bf16(lb + L.wph, 2 * D, rows, 2 * D, lb + L.wph_hi, lb + L.wph_lo, 2 * D, st));
       QAGNN_RETURN_IF(split_bf16(lb + L.w1, D, D, D, lb + L.w1_hi, lb + L.w1_lo, D, st));
       QAGNN_RETURN_IF(split_bf16(lb + L.w2, D, D, D, lb + L.w2_hi, lb + L.w2_lo, D, st));
     }

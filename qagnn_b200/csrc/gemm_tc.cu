@@ -105,6 +105,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Persistent kernel: one CTA per SM walks tiles (n fastest, so CTAs that share an A tile run together);
+// two 256-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,31 +114,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t w_bytes = (uint32_t)p.umma_n * BK * 2;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
   unsigned char* ctrl = smem + (size_t)p.stages * stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);       // [stages]
-  uint64_t* empty = full + p.stages;                        // [stages]
-  uint64_t* accbar = empty + p.stages;                      // [1] accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accbar + 1);
-
-  const int n0 = blockIdx.x * p.n_step;
-  const long long m0 = (long long)blockIdx.y * BM;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);       // [stages]  TMA -> MMA
+  uint64_t* empty = full + p.stages;                        // [stages]  MMA -> TMA
+  uint64_t* acc_full = empty + p.stages;                    // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;                       // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   // k-blocks across the (up to two) A segments
   int nkb_seg[2];
   nkb_seg[0] = (p.kseg[0] + BK - 1) / BK;
   nkb_seg[1] = p.nseg > 1 ? (p.kseg[1] + BK - 1) / BK : 0;
   const int nkb = nkb_seg[0] + nkb_seg[1];
+  const int n_tiles = (p.N + p.n_step - 1) / p.n_step;
+  const long long m_tiles = (p.M + BM - 1) / BM;
+  const long long total_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accbar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(p.tmem_cols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -148,18 +153,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        if (kb >= p.stages) mbar_wait(&empty[s], ((kb / p.stages) - 1) & 1);
-        const int seg = kb < nkb_seg[0] ? 0 : 1;
-        const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
-        const int k_glob = (seg == 0 ? 0 : p.kseg[0]) + k_in_seg;
-        unsigned char* st = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full[s], stage_bytes);
-        tma_load_2d(st, &p.a_hi[seg], k_in_seg, (int)m0, &full[s]);
-        tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, (int)m0, &full[s]);
-        tma_load_2d(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
-        tma_load_2d(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+      long long it = 0;  // k-block counter across tiles
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % n_tiles) * p.n_step;
+        const int m0 = (int)((tile / n_tiles) * BM);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % p.stages);
+          if (it >= p.stages) mbar_wait(&empty[s], (uint32_t)((it / p.stages) - 1) & 1u);
+          const int seg = kb < nkb_seg[0] ? 0 : 1;
+          const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
+          const int k_glob = (seg == 0 ? 0 : p.kseg[0]) + k_in_seg;
+          unsigned char* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          tma_load_2d(st, &p.a_hi[seg], k_in_seg, m0, &full[s]);
+          tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, m0, &full[s]);
+          tma_load_2d(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
+          tma_load_2d(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -167,106 +177,118 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(&full[s], (kb / p.stages) & 1);
-        tc_fence_after();
-        const int seg = kb < nkb_seg[0] ? 0 : 1;
-        const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
-        const int krem = p.kseg[seg] - k_in_seg;
-        const int nsteps = krem >= BK ? BK / 16 : (krem + 15) / 16;  // skip k-steps that are pure zero fill
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        for (int k = 0; k < nsteps; ++k) {
-          const uint64_t da_hi = umma_desc(sa + k * 32), da_lo = umma_desc(sa + a_bytes + k * 32);
-          const uint64_t dw_hi = umma_desc(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc(sa + 2 * a_bytes + w_bytes + k * 32);
-          umma_bf16(tmem_base, da_hi, dw_hi, idesc, (kb | k) != 0);
-          umma_bf16(tmem_base, da_hi, dw_lo, idesc, 1u);
-          umma_bf16(tmem_base, da_lo, dw_hi, idesc, 1u);
+      long long it = 0;
+      int ti = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        if (ti >= 2) {  // the epilogue must have drained this accumulator
+          mbar_wait(&acc_empty[acc], (uint32_t)((ti >> 1) - 1) & 1u);
+          tc_fence_after();
         }
-        umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = (int)(it % p.stages);
+          mbar_wait(&full[s], (uint32_t)(it / p.stages) & 1u);
+          tc_fence_after();
+          const int seg = kb < nkb_seg[0] ? 0 : 1;
+          const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
+          const int krem = p.kseg[seg] - k_in_seg;
+          const int nsteps = krem >= BK ? BK / 16 : (krem + 15) / 16;  // skip k-steps that are pure zero fill
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int k = 0; k < nsteps; ++k) {
+            const uint64_t da_hi = umma_desc(sa + k * 32), da_lo = umma_desc(sa + a_bytes + k * 32);
+            const uint64_t dw_hi = umma_desc(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc(sa + 2 * a_bytes + w_bytes + k * 32);
+            umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
+            umma_bf16(tmem_d, da_lo, dw_hi, idesc, 1u);
+          }
+          umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+        }
+        umma_commit(&acc_full[acc]);
       }
-      umma_commit(accbar);
     }
   } else {
     // ===================================== epilogue (warps 2..5) =====================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const long long row = m0 + quad * 32 + lane;
-    const int n_end = min(n0 + p.n_step, p.N);
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < p.umma_n && n0 + c0 < n_end; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (row >= p.M) continue;
-      const int col0 = n0 + c0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = v[i];
-        if (p.bias != nullptr && col0 + i < n_end) x += p.bias[col0 + i];
-        if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-        if (p.act == ACT_GELU) x = gelu_tanh(x);
-        v[i] = x;
-      }
-      if (p.c_f32 != nullptr) {
-        float* dst = p.c_f32 + row * p.ldc + col0;
-        if (col0 + 16 <= n_end && (p.ldc & 3) == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (col0 + i < n_end) dst[i] = v[i];
-        }
-      }
-      if (p.c_hm != nullptr) {
-        // logical column -> (which, head, j) of the head-major padded layout [3][H][M][DP], advanced incrementally.
-        // D and d even => a head starts on an even column, so (even, odd) column pairs never straddle heads.
-        const int D = p.hm.D, d = p.hm.d;
-        int which = col0 / D, hh = (col0 % D) / d, jj = (col0 % D) % d;
-        if ((d & 1) == 0 && (D & 1) == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float* dst = p.c_hm + ((size_t)(which * p.hm.H + hh) * p.M + row) * p.hm.DP + jj;
-            if (col0 + i + 1 < n_end) *reinterpret_cast<float2*>(dst) = make_float2(v[i], v[i + 1]);
-            else if (col0 + i < n_end) *dst = v[i];
-            jj += 2;
-            if (jj >= d) { jj = 0; if (++hh == p.hm.H) { hh = 0; ++which; } }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (col0 + i < n_end) p.c_hm[((size_t)(which * p.hm.H + hh) * p.M + row) * p.hm.DP + jj] = v[i];
-            if (++jj == d) { jj = 0; if (++hh == p.hm.H) { hh = 0; ++which; } }
-          }
-        }
-      }
-      if (p.c_hi != nullptr) {
-        __nv_bfloat16 hi[16], lo[16];
+    int ti = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      const int n0 = (int)(tile % n_tiles) * p.n_step;
+      const long long row = (tile / n_tiles) * BM + quad * 32 + lane;
+      const int n_end = min(n0 + p.n_step, p.N);
+      mbar_wait(&acc_full[acc], (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
+      for (int c0 = 0; c0 < p.umma_n && n0 + c0 < n_end; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (row >= p.M) continue;
+        const int col0 = n0 + c0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          hi[i] = __float2bfloat16_rn(v[i]);
-          lo[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hi[i]));
+          float x = v[i];
+          if (p.bias != nullptr && col0 + i < n_end) x += p.bias[col0 + i];
+          if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+          if (p.act == ACT_GELU) x = gelu_tanh(x);
+          v[i] = x;
         }
-        __nv_bfloat16* dh = p.c_hi + row * p.ldp + col0;
-        __nv_bfloat16* dl = p.c_lo + row * p.ldp + col0;
-        if (col0 + 16 <= n_end && (p.ldp & 7) == 0) {
-          *reinterpret_cast<uint4*>(dh) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(dh + 8) = *reinterpret_cast<const uint4*>(hi + 8);
-          *reinterpret_cast<uint4*>(dl) = *reinterpret_cast<const uint4*>(lo);
-          *reinterpret_cast<uint4*>(dl + 8) = *reinterpret_cast<const uint4*>(lo + 8);
-        } else {
+        if (p.c_f32 != nullptr) {
+          float* dst = p.c_f32 + row * p.ldc + col0;
+          if (col0 + 16 <= n_end && (p.ldc & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (col0 + i < n_end) { dh[i] = hi[i]; dl[i] = lo[i]; }
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < n_end) dst[i] = v[i];
+          }
+        }
+        if (p.c_hm != nullptr) {
+          // padded head-major output: the weight rows were laid out as [3][H][DP] (zero rows in the pads), so GEMM
+          // column c = (which*H + h)*DP + j maps to slab (which*H + h), offset row*DP + j; DP % 4 == 0 keeps every
+          // float4 inside one head and 16-byte aligned
+          const int DP = p.hm.DP;
+          int slab = col0 / DP, jj = col0 % DP;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (col0 + i < n_end)
+              *reinterpret_cast<float4*>(p.c_hm + ((size_t)slab * p.M + row) * DP + jj) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            jj += 4;
+            if (jj >= DP) { jj = 0; ++slab; }
+          }
+        }
+        if (p.c_hi != nullptr) {
+          __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hi[i] = __float2bfloat16_rn(v[i]);
+            lo[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hi[i]));
+          }
+          __nv_bfloat16* dh = p.c_hi + row * p.ldp + col0;
+          __nv_bfloat16* dl = p.c_lo + row * p.ldp + col0;
+          if (col0 + 16 <= n_end && (p.ldp & 7) == 0) {
+            *reinterpret_cast<uint4*>(dh) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(dh + 8) = *reinterpret_cast<const uint4*>(hi + 8);
+            *reinterpret_cast<uint4*>(dl) = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(dl + 8) = *reinterpret_cast<const uint4*>(lo + 8);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < n_end) { dh[i] = hi[i]; dl[i] = lo[i]; }
+          }
         }
       }
+      // accumulator drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -348,22 +370,27 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   if (!gemm_tc_shape_ok(K1, K2, A1.ld, A2.ld, W.ld, N)) return QAGNN_ERR_UNSUPPORTED;
   TcParams p;
   memset(&p, 0, sizeof(p));
-  const int n_tiles = (N + 255) / 256;
+  int n_tiles = (N + 255) / 256;
   p.n_step = (N + n_tiles - 1) / n_tiles;
   p.n_step = (p.n_step + 7) / 8 * 8;
+  if (out.hm_buf != nullptr) {  // one `which` (Q / Kx / Mx) per tile: H*DP padded columns
+    p.n_step = out.hm.H * out.hm.DP;
+    if (p.n_step > 256 || p.n_step % 16 != 0 || N % p.n_step != 0) return QAGNN_ERR_UNSUPPORTED;
+    n_tiles = N / p.n_step;
+  }
   p.umma_n = (p.n_step + 15) / 16 * 16;
   p.N = N;
   p.M = M;
   p.nseg = K2 > 0 ? 2 : 1;
   p.kseg[0] = K1;
   p.kseg[1] = K2;
-  p.tmem_cols = p.umma_n <= 32 ? 32 : p.umma_n <= 64 ? 64 : p.umma_n <= 128 ? 128 : 256;
+  p.tmem_cols = 512;
   const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  const size_t smem_bytes = stages * stage_bytes + (2 * stages + 4) * 8 + 16;
   bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM);
   if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM);
   ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n);
@@ -382,7 +409,14 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
     QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr = smem_bytes;
   }
-  dim3 grid((unsigned)n_tiles, (unsigned)((M + BM - 1) / BM));
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    QAGNN_CHECK_CUDA(cudaGetDevice(&dev));
+    QAGNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long total_tiles = (long long)n_tiles * ((M + BM - 1) / BM);
+  const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);
   gemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
   QAGNN_CHECK_LAUNCH();
   return QAGNN_OK;
