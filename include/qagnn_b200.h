@@ -167,6 +167,15 @@ int32_t qagnn_mp_forward(const qagnn_shape *shape, const float *H_in, const int6
                          const float *node_score, const void *prep, const void *folded, float *out,
                          float *x_layers_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* A stand-alone dense layer on the same tensor-core path the forward uses (diagnostics / tests):
+ *   C[M,N] (ldc) = act( [A1 | A2] @ W^T + bias ),  fp32 row-major operands, W [N, K1+K2] (ldw), act 0/1/2 = none/ReLU/GELU(tanh).
+ * Splits the operands into bf16 hi/lo planes in `workspace` and runs the tcgen05 3-pass GEMM; returns
+ * QAGNN_ERR_UNSUPPORTED when the tensor-core path cannot take the shape (K or ld not multiples of 8). */
+size_t qagnn_linear_workspace_bytes(int64_t M, int32_t N, int32_t K1, int32_t K2);
+int32_t qagnn_linear_bf16x3(const float *A1, int32_t lda1, int32_t K1, const float *A2, int32_t lda2, int32_t K2,
+                            const float *W, int32_t ldw, const float *bias, float *C, int32_t ldc, int64_t M, int32_t N,
+                            int32_t act, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Launch counters since load (kernels this library enqueued); for bench.py's gpu_launches. */
 int64_t qagnn_launch_count(void);
 

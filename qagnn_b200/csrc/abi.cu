@@ -365,3 +365,33 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   return sgemm_tn(H_in, s.D, s.D, x, s.D, s.D, f + L.vcat, 2 * s.D, f + L.vbias, out, s.D, s.N, s.D, ACT_GELU, st);
 }
+
+extern "C" size_t qagnn_linear_workspace_bytes(int64_t M, int32_t N, int32_t K1, int32_t K2) {
+  if (M <= 0 || N <= 0 || K1 <= 0 || K2 < 0) return 0;
+  const size_t K = (size_t)K1 + K2;
+  return align_up(2 * 2 * ((size_t)M * K + (size_t)N * K) + 4 * 1024);
+}
+
+extern "C" int32_t qagnn_linear_bf16x3(const float* A1, int32_t lda1, int32_t K1, const float* A2, int32_t lda2, int32_t K2,
+                                       const float* Wt, int32_t ldw, const float* bias, float* C, int32_t ldc, int64_t M,
+                                       int32_t N, int32_t act, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!A1 || !Wt || !C || !workspace || M <= 0 || N <= 0 || K1 <= 0 || K2 < 0 || (K2 > 0 && !A2)) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (act < 0 || act > 2) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < qagnn_linear_workspace_bytes(M, N, K1, K2)) return QAGNN_ERR_WORKSPACE;
+  if (!gemm_tc_available() || !gemm_tc_shape_ok(K1, K2, K1, K2, K1 + K2, N)) return QAGNN_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)workspace;
+  auto take = [&](size_t elems) { char* r = w; w += align_up(elems * 2); return (void*)r; };
+  const int K = K1 + K2;
+  void *a1h = take((size_t)M * K1), *a1l = take((size_t)M * K1);
+  void *a2h = K2 ? take((size_t)M * K2) : nullptr, *a2l = K2 ? take((size_t)M * K2) : nullptr;
+  void *wh = take((size_t)N * K), *wl = take((size_t)N * K);
+  QAGNN_RETURN_IF(split_bf16(A1, lda1, M, K1, a1h, a1l, K1, st));
+  if (K2) QAGNN_RETURN_IF(split_bf16(A2, lda2, M, K2, a2h, a2l, K2, st));
+  QAGNN_RETURN_IF(split_bf16(Wt, ldw, N, K, wh, wl, K, st));
+  TcOperand o1{a1h, a1l, K1, K1}, o2{a2h, a2l, K2, K2}, ow{wh, wl, K, K};
+  TcOutput out{};
+  out.f32 = C;
+  out.ldc = ldc;
+  return gemm_tc(o1, o2, ow, bias, M, N, (Act)act, out, st);
+}
