@@ -43,6 +43,7 @@ struct alignas(64) TcParams {
   __nv_bfloat16 *c_hi, *c_lo;
   int ldp;
   unsigned tmem_cols;
+  int debug;  // QAGNN_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip TMEM loads, 4 skip MMAs (timing experiments)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +108,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Persistent kernel: one CTA per SM walks tiles (n fastest, so CTAs that share an A tile run together);
 // two 256-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int kStagePitch = 34;  // floats; even -> float2-aligned rows for the bf16-plane path
+constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int k = 0; k < nsteps; ++k) {
             const uint64_t da_hi = umma_desc(sa + k * 32), da_lo = umma_desc(sa + a_bytes + k * 32);
             const uint64_t dw_hi = umma_desc(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc(sa + 2 * a_bytes + w_bytes + k * 32);
+            if (p.debug & 4) continue;
             umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
             umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
             umma_bf16(tmem_d, da_lo, dw_hi, idesc, 1u);
@@ -209,74 +229,80 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ===================================== epilogue (warps 2..5) =====================================
+    // TMEM -> registers (thread = row) -> bias/activation -> per-warp smem transpose -> coalesced global stores
+    // (lanes = consecutive columns of one row).  Thread-per-row stores ran at ~1 TB/s; see profiles/r1_gemm_tc.md.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 1024) + (size_t)(warp - 2) * (kStageBytesPerWarp / 4);
     int ti = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
       const int n0 = (int)(tile % n_tiles) * p.n_step;
-      const long long row = (tile / n_tiles) * BM + quad * 32 + lane;
+      const long long row0 = (tile / n_tiles) * BM + quad * 32;  // first row of this warp
       const int n_end = min(n0 + p.n_step, p.N);
       mbar_wait(&acc_full[acc], (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
-      for (int c0 = 0; c0 < p.umma_n && n0 + c0 < n_end; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        if (row >= p.M) continue;
-        const int col0 = n0 + c0;
+      for (int c0 = 0; c0 < p.umma_n && n0 + c0 < n_end; c0 += 32) {
+        const int ncol = min(32, p.umma_n - c0);  // 32 or 16 (umma_n is a multiple of 16)
+        float v[32];
+        if (p.debug & 2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        } else if (ncol == 32) {
+          tmem_ld32(taddr + (uint32_t)c0, v);
+        } else {
+          float t[16];
+          tmem_ld16(taddr + (uint32_t)c0, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = t[i]; v[i + 16] = 0.f; }
+        }
+        if (p.debug & 1) continue;
+        const int col0 = n0 + c0;
+        // stage (thread = row): bias + activation, then write the row into the transpose buffer
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
           float x = v[i];
-          if (p.bias != nullptr && col0 + i < n_end) x += p.bias[col0 + i];
+          if (p.bias != nullptr && col0 + i < n_end) x += __ldg(p.bias + col0 + i);
           if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
           if (p.act == ACT_GELU) x = gelu_tanh(x);
-          v[i] = x;
+          stg[lane * kStagePitch + i] = x;
         }
-        if (p.c_f32 != nullptr) {
-          float* dst = p.c_f32 + row * p.ldc + col0;
-          if (col0 + 16 <= n_end && (p.ldc & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (col0 + i < n_end) dst[i] = v[i];
-          }
+        __syncwarp();
+        const int col = col0 + lane;
+        if (p.c_f32 != nullptr && lane < ncol && col < n_end) {
+          float* dst = p.c_f32 + col;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r)
+            if (row0 + r < p.M) dst[(row0 + r) * p.ldc] = stg[r * kStagePitch + lane];
         }
-        if (p.c_hm != nullptr) {
-          // padded head-major output: the weight rows were laid out as [3][H][DP] (zero rows in the pads), so GEMM
-          // column c = (which*H + h)*DP + j maps to slab (which*H + h), offset row*DP + j; DP % 4 == 0 keeps every
-          // float4 inside one head and 16-byte aligned
+        if (p.c_hm != nullptr && lane < ncol && col < n_end) {
+          // padded head-major output: weight rows are laid out [3][H][DP], so column c = slab*DP + j
           const int DP = p.hm.DP;
-          int slab = col0 / DP, jj = col0 % DP;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            if (col0 + i < n_end)
-              *reinterpret_cast<float4*>(p.c_hm + ((size_t)slab * p.M + row) * DP + jj) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            jj += 4;
-            if (jj >= DP) { jj = 0; ++slab; }
-          }
+          float* dst = p.c_hm + (size_t)(col / DP) * p.M * DP + (col % DP);
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r)
+            if (row0 + r < p.M) dst[(row0 + r) * DP] = stg[r * kStagePitch + lane];
         }
         if (p.c_hi != nullptr) {
-          __nv_bfloat16 hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            hi[i] = __float2bfloat16_rn(v[i]);
-            lo[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hi[i]));
-          }
-          __nv_bfloat16* dh = p.c_hi + row * p.ldp + col0;
-          __nv_bfloat16* dl = p.c_lo + row * p.ldp + col0;
-          if (col0 + 16 <= n_end && (p.ldp & 7) == 0) {
-            *reinterpret_cast<uint4*>(dh) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(dh + 8) = *reinterpret_cast<const uint4*>(hi + 8);
-            *reinterpret_cast<uint4*>(dl) = *reinterpret_cast<const uint4*>(lo);
-            *reinterpret_cast<uint4*>(dl + 8) = *reinterpret_cast<const uint4*>(lo + 8);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (col0 + i < n_end) { dh[i] = hi[i]; dl[i] = lo[i]; }
+          // two rows per instruction: lanes 0-15 -> row 2q, lanes 16-31 -> row 2q+1, two columns per lane
+          const int j2 = 2 * (lane & 15);
+          if (j2 < ncol && col0 + j2 < n_end) {
+#pragma unroll 4
+            for (int q = 0; q < 16; ++q) {
+              const int r = 2 * q + (lane >> 4);
+              if (row0 + r >= p.M) continue;
+              const float2 x = *reinterpret_cast<const float2*>(stg + r * kStagePitch + j2);
+              __nv_bfloat162 hh, ll;
+              hh.x = __float2bfloat16_rn(x.x);
+              hh.y = __float2bfloat16_rn(x.y);
+              ll.x = __float2bfloat16_rn(x.x - __bfloat162float(hh.x));
+              ll.y = __float2bfloat16_rn(x.y - __bfloat162float(hh.y));
+              *reinterpret_cast<__nv_bfloat162*>(p.c_hi + (row0 + r) * p.ldp + col0 + j2) = hh;
+              *reinterpret_cast<__nv_bfloat162*>(p.c_lo + (row0 + r) * p.ldp + col0 + j2) = ll;
+            }
           }
         }
+        __syncwarp();
       }
       // accumulator drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -386,17 +412,19 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.kseg[1] = K2;
   p.tmem_cols = 512;
   const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
-  int stages = (int)((220 * 1024) / stage_bytes);
+  int stages = (int)((226 * 1024 - 1024 - 4 * kStageBytesPerWarp) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem_bytes = stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+  // operand ring | 1 KB of barriers | 4 per-warp transpose buffers
+  const size_t smem_bytes = stages * stage_bytes + 1024 + 4 * (size_t)kStageBytesPerWarp;
   bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM);
   if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM);
   ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n);
   if (!ok) return QAGNN_ERR_CUDA;
   p.bias = bias;
   p.act = (int)act;
+  { const char* e = getenv("QAGNN_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.c_f32 = out.f32;
   p.ldc = out.ldc;
   p.c_hm = out.hm_buf;
