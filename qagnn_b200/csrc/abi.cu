@@ -134,7 +134,7 @@ int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
     if (tiled) {
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
-                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, st));
+                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, nullptr, nullptr, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
                                              ws + W.alpha, aggr, alpha_out, st));
@@ -166,7 +166,8 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
   const int D = s.D;
   const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
   float* qkm = ws + W.qkm;
-  float* aggr = aggr_out ? aggr_out : ws + W.aggr;
+  const bool fused_split = tiled && (D / s.H) % 2 == 0;  // the tiled kernel emits the bf16 planes of aggr itself
+  float* aggr = aggr_out ? aggr_out : (fused_split ? nullptr : ws + W.aggr);
   {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
     ProfScope ps(QAGNN_PROF_PROJECTION, st);
     TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D};
@@ -188,7 +189,8 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
     if (tiled) {
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
-                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, st));
+                                                      ws + W.score, ws + W.alpha, aggr, alpha_out,
+                                                      fused_split ? ws + W.ap_hi : nullptr, ws + W.ap_lo, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
                                              ws + W.alpha, aggr, alpha_out, st));
@@ -196,7 +198,7 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
   }
   {  // node MLP: Linear -> BatchNorm(eval, folded) -> ReLU -> Linear          (:443, :408)
     ProfScope ps(QAGNN_PROF_NODE_MLP, st);
-    QAGNN_RETURN_IF(split_bf16(aggr, D, s.N, D, ws + W.ap_hi, ws + W.ap_lo, D, st));
+    if (!fused_split) QAGNN_RETURN_IF(split_bf16(aggr, D, s.N, D, ws + W.ap_hi, ws + W.ap_lo, D, st));
     TcOperand A{ws + W.ap_hi, ws + W.ap_lo, D, D}, none{nullptr, nullptr, 0, 0};
     TcOperand W1{lb + L.w1_hi, lb + L.w1_lo, D, D}, W2{lb + L.w2_hi, lb + L.w2_lo, D, D};
     TcOutput o1{};

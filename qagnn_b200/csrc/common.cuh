@@ -141,7 +141,8 @@ inline int head_dim_padded(int d) { return (d + 3) / 4 * 4; }
 bool headtile_supported(const qagnn_shape& s);
 int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
                                         const float* qkmh, const float* keh, const float* meh, float* score,
-                                        float* alpha, float* aggr, float* alpha_out, cudaStream_t st);
+                                        float* alpha, float* aggr, float* alpha_out, void* aggr_hi, void* aggr_lo,
+                                        cudaStream_t st);
 int32_t zero_head_pads(const qagnn_shape& s, float* qkmh, cudaStream_t st);
 
 int32_t launch_message_passing(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,

@@ -20,6 +20,8 @@
 //     iteration for ILP; the softmax runs lane-parallel over the node's edges after the loop.
 // Node rows come from the head-major padded projection layout [3][H][N][DP] written by the
 // projection GEMM, so a tile is one contiguous n*DP*4-byte bulk copy.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace qagnn {
@@ -32,6 +34,7 @@ struct HeadTileParams {
   const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *pk_tgt, *tpos, *perm_src;
   const float *qkmh, *keh, *meh;
   float *score, *alpha, *aggr, *alpha_out;
+  void *aggr_hi, *aggr_lo;  // optional split-bf16 planes of aggr [N, D] (A operand of the node-MLP GEMM)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -360,21 +363,40 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
         }
       }
       if (nvalid) {
-        float* out = p.aggr + ((int64_t)g * p.n + vl) * p.D + (size_t)h * p.d;
+        const size_t obase = ((int64_t)g * p.n + vl) * p.D + (size_t)h * p.d;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           const int c0 = 4 * (l8 + 8 * k);
           if (!cvalid[k] || c0 >= p.d) continue;
-          if ((p.d & 3) == 0 && (p.D & 3) == 0) {
-            *reinterpret_cast<float4*>(out + c0) = make_float4(acc[k][0].x, acc[k][0].y, acc[k][1].x, acc[k][1].y);
-          } else if ((p.d & 1) == 0) {
-            *reinterpret_cast<float2*>(out + c0) = acc[k][0];
-            if (c0 + 2 < p.d) *reinterpret_cast<float2*>(out + c0 + 2) = acc[k][1];
-          } else {
-            out[c0] = acc[k][0].x;
-            if (c0 + 1 < p.d) out[c0 + 1] = acc[k][0].y;
-            if (c0 + 2 < p.d) out[c0 + 2] = acc[k][1].x;
-            if (c0 + 3 < p.d) out[c0 + 3] = acc[k][1].y;
+          const float v0 = acc[k][0].x, v1 = acc[k][0].y, v2 = acc[k][1].x, v3 = acc[k][1].y;
+          if (p.aggr != nullptr) {
+            float* out = p.aggr + obase;
+            if ((p.d & 3) == 0 && (p.D & 3) == 0) {
+              *reinterpret_cast<float4*>(out + c0) = make_float4(v0, v1, v2, v3);
+            } else if ((p.d & 1) == 0) {
+              *reinterpret_cast<float2*>(out + c0) = make_float2(v0, v1);
+              if (c0 + 2 < p.d) *reinterpret_cast<float2*>(out + c0 + 2) = make_float2(v2, v3);
+            } else {
+              out[c0] = v0;
+              if (c0 + 1 < p.d) out[c0 + 1] = v1;
+              if (c0 + 2 < p.d) out[c0 + 2] = v2;
+              if (c0 + 3 < p.d) out[c0 + 3] = v3;
+            }
+          }
+          if (p.aggr_hi != nullptr) {  // d even (D % 8 == 0 on this path): bf16x2 pairs stay 4-byte aligned
+            __nv_bfloat16* oh = (__nv_bfloat16*)p.aggr_hi + obase + c0;
+            __nv_bfloat16* ol = (__nv_bfloat16*)p.aggr_lo + obase + c0;
+            __nv_bfloat162 h01, l01, h23, l23;
+            h01.x = __float2bfloat16_rn(v0); h01.y = __float2bfloat16_rn(v1);
+            l01.x = __float2bfloat16_rn(v0 - __bfloat162float(h01.x)); l01.y = __float2bfloat16_rn(v1 - __bfloat162float(h01.y));
+            *reinterpret_cast<__nv_bfloat162*>(oh) = h01;
+            *reinterpret_cast<__nv_bfloat162*>(ol) = l01;
+            if (c0 + 2 < p.d) {
+              h23.x = __float2bfloat16_rn(v2); h23.y = __float2bfloat16_rn(v3);
+              l23.x = __float2bfloat16_rn(v2 - __bfloat162float(h23.x)); l23.y = __float2bfloat16_rn(v3 - __bfloat162float(h23.y));
+              *reinterpret_cast<__nv_bfloat162*>(oh + 2) = h23;
+              *reinterpret_cast<__nv_bfloat162*>(ol + 2) = l23;
+            }
           }
         }
       }
@@ -464,7 +486,8 @@ int32_t zero_head_pads(const qagnn_shape& s, float* qkmh, cudaStream_t st) {
 
 int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& L,
                                         const float* qkmh, const float* keh, const float* meh, float* score,
-                                        float* alpha, float* aggr, float* alpha_out, cudaStream_t st) {
+                                        float* alpha, float* aggr, float* alpha_out, void* aggr_hi, void* aggr_lo,
+                                        cudaStream_t st) {
   const HeadTilePlan plan = make_plan(s);
   if (!plan.ok) return QAGNN_ERR_UNSUPPORTED;
   auto I = [&](size_t off) { return (const int32_t*)((const char*)prep_base + off); };
@@ -475,6 +498,8 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   p.rowptr_src = I(L.rowptr_src); p.rowptr_tgt = I(L.rowptr_tgt); p.pk_src = I(L.pk_src); p.pk_tgt = I(L.pk_tgt);
   p.tpos = I(L.csr_src_tpos); p.perm_src = I(L.perm_src);
   p.qkmh = qkmh; p.keh = keh; p.meh = meh; p.score = score; p.alpha = alpha; p.aggr = aggr; p.alpha_out = alpha_out;
+  p.aggr_hi = (s.D % 2 == 0 && (s.D / s.H) % 2 == 0) ? aggr_hi : nullptr; p.aggr_lo = aggr_lo;
+  if (aggr_hi != nullptr && p.aggr_hi == nullptr) return QAGNN_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)(plan.S * s.H), block = (unsigned)(plan.W + 1) * 32;
   if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1>(p, plan, grid, block, st);
   if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2>(p, plan, grid, block, st);
