@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-graphs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch the ~60 kernels of a step one by one")
     return ap.parse_args()
 
 
@@ -184,14 +185,32 @@ def run_b200_arm(args):
     out_host = torch.empty(B, n, D, dtype=torch.float32).pin_memory()
     gathered = torch.empty(world * B, D, device=dev) if world > 1 else None
 
+    # resident arm: graph prep + all layers replayed as ONE CUDA graph (inputs stay in the same device buffers);
+    # indices are validated once before the capture.  Falls back to per-kernel launches if capture is unavailable.
+    launch_mode = "per-kernel launches"
+    if not args.no_cuda_graph:
+        try:
+            mod.use_cuda_graph = True
+            mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+            torch.cuda.synchronize()
+            launch_mode = "one CUDA graph per step (prep + 5 layers + epilogue)"
+        except Exception as exc:  # noqa: BLE001
+            mod.use_cuda_graph = False
+            mod._graphs.clear()
+            launch_mode = f"per-kernel launches (CUDA graph capture failed: {type(exc).__name__})"
+
     def step_resident():
         out = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
         if world > 1:  # the path's single collective: all-gather of the pooled (context-node) vectors
             dist.all_gather_into_tensor(gathered, out[:, 0].contiguous())
         return out
 
+    e2e_dev = {k_: torch.empty_like(v, device=dev) for k_, v in host.items()}  # static staging buffers (graph replay)
+
     def step_e2e():
-        dd = {k_: v.to(dev, non_blocking=True) for k_, v in host.items()}
+        for k_, v in host.items():
+            e2e_dev[k_].copy_(v, non_blocking=True)
+        dd = e2e_dev
         out = mod(dd["H"], (dd["edge_index"], dd["edge_type"]), dd["node_type"], dd["node_score"])
         if world > 1:
             dist.all_gather_into_tensor(gathered, out[:, 0].contiguous())
@@ -229,10 +248,17 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms_total, _, _ = timed(step_resident, args.steps)
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    # kernel-level pass: the same K steps launched kernel by kernel with the library's CUDA-event stage timers on the
+    # launching stream (events cannot be timed inside a replayed graph); feeds `roofline`, `stages`, `gpu_launches`
+    graphed = mod.use_cuda_graph
+    mod.use_cuda_graph = False
+    step_resident()
+    ms_eager, launches, prof = timed(step_resident, args.steps, profile=True)
+    mod.use_cuda_graph = graphed
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
@@ -269,17 +295,22 @@ def run_b200_arm(args):
                    "shards, one NCCL all-gather of pooled vectors)" if world > 1 else "single GPU",
                    "l2": f"no flush: a step streams the {lib.qagnn_forward_workspace_bytes(_lib.C.byref(mod._shape(N, E, n))) / 1e6:.0f} MB "
                          "workspace + 51 MB inputs, > 126 MB L2", "step": "graph prep + 5 x (projection, message passing, "
-                   "node MLP) + Vh/Vx epilogue, inputs resident in HBM"},
+                   "node MLP) + Vh/Vx epilogue, inputs resident in HBM", "launch": launch_mode},
         "qa_pairs_per_s": world * B / (ms_step * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "qagnn_b200.QAGNN_Message_Passing.forward on pinned host tensors (H2D of H/edge_index/edge_type/"
                        "node_type/node_score, forward, D2H of the [B,n,D] output)"},
         "gpu_launches": int(launches),
+        "gpu_launches_note": "kernels of libqagnn_b200.so enqueued by the K steps of the kernel-level pass (the CUDA graph "
+                             "of the headline pass replays the same kernel nodes)",
+        "ms_per_step_per_kernel_launches": ms_eager / args.steps,
         "roofline": {"kernel": "message passing (mp_scores_kernel + mp_aggregate_kernel), one GATConvE layer",
                      "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "avg_launch_ms": mp_avg_ms,
-                     "launches_timed": int(mp_cnt), "traffic": None},
+                     "launches_timed": int(mp_cnt),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_mp_headtile_ncu.md)
+                     "traffic": 187043328 if world == 1 else None},
         "stages": stages,
         "clocks": clocks,
     }

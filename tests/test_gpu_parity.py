@@ -212,3 +212,69 @@ def test_cross_graph_edge_is_rejected_when_n_per_graph_is_given():
     GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=0)  # legal for a general graph
     with pytest.raises(IndexError):
         GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=10)
+
+
+def test_large_graph_general_path_matches_oracle():
+    """Stress-shaped input (BASELINE.json configs[4] scaled down): one big graph per batch entry, H=8 — too large for
+    the shared-memory tiles, so this exercises the general CSR kernels + tensor-core GEMMs end to end."""
+    n, e, D, Hh_, k = 600, 6000, 256, 8, 2
+    inp = O.synth_graph_batch(2, n, e, D, 38, seed=21)
+    sd = O.random_state_dict(1, D, 4, 38, "peaky", seed=21)
+    x = inp["H"].view(-1, D).contiguous()
+    extra = torch.randn(x.shape, generator=torch.Generator().manual_seed(5)) * 0.5
+    nt = inp["node_type"].view(-1)
+    ref_out, ei2, ref_alpha, _ = O.gatconve_forward(sd, "gnn_layers.0", x, inp["edge_index"], inp["edge_type"], nt, extra,
+                                                    4, 38, head_count=Hh_)
+    enc = torch.nn.Sequential(torch.nn.Linear(38 + 1 + 8, D), torch.nn.BatchNorm1d(D), torch.nn.ReLU(), torch.nn.Linear(D, D))
+    layer = qagnn_b200.GATConvE(None, D, 4, 38, enc, head_count=Hh_).eval()
+    layer.load_state_dict({k_[len("gnn_layers.0."):]: v for k_, v in sd.items() if k_.startswith("gnn_layers.0.")})
+    layer = layer.to(DEV)
+    out, (ei_g, alpha) = layer(x.to(DEV), inp["edge_index"].to(DEV), inp["edge_type"].to(DEV), nt.to(DEV), extra.to(DEV),
+                               return_attention_weights=True)
+    assert torch.equal(ei_g.cpu(), ei2)
+    Hh.assert_close(alpha, ref_alpha, "alpha")
+    Hh.assert_close(out, ref_out, "out")
+
+
+def test_lm_qagnn_forward_api_with_packed_and_nested_adjacency():
+    """LM_QAGNN.forward keeps the reference's positional-input API (modeling_qagnn.py:207-251): nested
+    [batch][choice] adjacency lists and the packed form give identical logits; the decoder part matches the oracle."""
+    from transformers import RobertaConfig
+    from qagnn_b200.data import pack_adj
+    torch.manual_seed(0)
+    cfg = RobertaConfig(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                        max_position_embeddings=40)
+    bs, nc, n, D, k = 3, 5, 20, 64, 2
+    model = qagnn_b200.LM_QAGNN(None, "roberta-tiny", k, 4, 38, n_concept=200, concept_dim=D, concept_in_dim=D,
+                                n_attention_head=2, fc_dim=D, n_fc_layer=0, p_emb=0.2, p_gnn=0.2, p_fc=0.2,
+                                init_range=0.02, encoder_config={"config": cfg}).eval().to(DEV)
+    g = torch.Generator().manual_seed(1)
+    input_ids = torch.randint(3, 100, (bs, nc, 16), generator=g)
+    attn = torch.ones(bs, nc, 16, dtype=torch.long)
+    ttype = torch.zeros(bs, nc, 16, dtype=torch.long)
+    omask = torch.zeros(bs, nc, 16, dtype=torch.long)
+    inp = O.synth_graph_batch(bs * nc, n, 50, D, 38, seed=3, realistic=True)
+    concept_ids = torch.randint(1, 201, (bs, nc, n), generator=g); concept_ids[:, :, 0] = 0
+    ei_nested, et_nested = [], []
+    for b in range(bs):
+        ei_row, et_row = [], []
+        for c in range(nc):
+            gi = b * nc + c
+            sel = (inp["edge_index"][0] >= gi * n) & (inp["edge_index"][0] < (gi + 1) * n)
+            ei_row.append((inp["edge_index"][:, sel] - gi * n).to(DEV)); et_row.append(inp["edge_type"][sel].to(DEV))
+        ei_nested.append(ei_row); et_nested.append(et_row)
+    dec_in = (concept_ids.to(DEV), inp["node_type"].view(bs, nc, n).to(DEV), inp["node_score"].view(bs, nc, n, 1).to(DEV),
+              inp["adj_lengths"].view(bs, nc).to(DEV))
+    lm_in = (input_ids.to(DEV), attn.to(DEV), ttype.to(DEV), omask.to(DEV))
+    with torch.no_grad():
+        logits, pool_attn = model(*lm_in, *dec_in, ei_nested, et_nested)
+        packed = pack_adj([[e.cpu() for e in r] for r in ei_nested], [[e.cpu() for e in r] for r in et_nested], n)
+        logits_p, _ = model(*lm_in, *dec_in, packed.to(DEV), None)
+        sent_vecs, _ = model.encoder(*[x.view(bs * nc, -1) for x in lm_in])
+    assert logits.shape == (bs, nc) and pool_attn.shape == (2 * bs * nc, n)
+    assert torch.equal(logits, logits_p)
+    sd = {k_: v.cpu() for k_, v in model.decoder.state_dict().items()}
+    ref_logits, _, _ = O.qagnn_decoder_forward(sd, sent_vecs.cpu(), concept_ids.view(bs * nc, n), inp["node_type"],
+                                               inp["node_score"], inp["adj_lengths"], inp["edge_index"], inp["edge_type"],
+                                               k, 4, 38, 2, 0)
+    Hh.assert_close(logits.view(-1, 1), ref_logits, "LM_QAGNN logits vs oracle decoder")
