@@ -26,7 +26,9 @@ namespace qagnn {
 namespace {
 
 constexpr int BM = 128;     // rows per CTA tile = UMMA M
-constexpr int BK = 64;      // bf16 per k-block = 128 bytes = one swizzle span
+// k-block width in bf16: 64 (128-byte swizzle span, 2 stages of ~85 KB) or 32 (64-byte span, 4 stages of ~43 KB).
+// The ring is latency bound (one stage = TMA round trip + its MMAs), so more, smaller stages move more bytes per
+// second, and the K = 200 tail block wastes half as much (profiles/r1_gemm_tc.md).
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 // warps 0-7: epilogue (TMEM lane quadrant = warp id % 4, two warps per quadrant alternate 32-column chunks: with one
@@ -84,9 +86,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 | LBO=1 | SBO=64 | version=1 | layout=SWIZZLE_128B)
+template <int BK>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  // rows of BK*2 bytes; 8-row groups (SBO) 8*BK*2 bytes apart; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+  const uint32_t hi = (uint32_t)(8 * BK * 2 / 16) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
   return ((uint64_t)hi << 32) | lo;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -140,7 +144,7 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 constexpr int kStagePitch = 34;  // floats; even -> float2-aligned rows for the bf16-plane path
 constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
 
-template <int ACT>
+template <int ACT, int BK>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int nsteps = krem >= BK ? BK / 16 : (krem + 15) / 16;  // skip k-steps that are pure zero fill
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           for (int k = 0; k < nsteps; ++k) {
-            const uint64_t da_hi = umma_desc(sa + k * 32), da_lo = umma_desc(sa + a_bytes + k * 32);
-            const uint64_t dw_hi = umma_desc(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc(sa + 2 * a_bytes + w_bytes + k * 32);
+            const uint64_t da_hi = umma_desc<BK>(sa + k * 32), da_lo = umma_desc<BK>(sa + a_bytes + k * 32);
+            const uint64_t dw_hi = umma_desc<BK>(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc<BK>(sa + 2 * a_bytes + w_bytes + k * 32);
             if (p.debug & 4) continue;
             umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
             umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
@@ -386,7 +390,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // [rows, K] bf16 row-major (ld elements) -> 2-D tensor map with a {64, box_rows} box, 128-byte swizzle
-bool make_map(CUtensorMap* m, const void* base, long long rows, int K, int ld, int box_rows) {
+bool make_map(CUtensorMap* m, const void* base, long long rows, int K, int ld, int box_rows, int BK) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -394,7 +398,8 @@ bool make_map(CUtensorMap* m, const void* base, long long rows, int K, int ld, i
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -445,16 +450,20 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.kseg[0] = K1;
   p.kseg[1] = K2;
   p.tmem_cols = 512;
+  static const int BK = [] {
+    const char* e = getenv("QAGNN_TC_BK");
+    return (e && atoi(e) == 64) ? 64 : 32;
+  }();
   const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
   int stages = (int)((226 * 1024 - 1024 - kEpiWarps * kStageBytesPerWarp) / stage_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 6) stages = 6;
   if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
   p.stages = stages;
   // operand ring | 1 KB of barriers | 4 per-warp transpose buffers
   const size_t smem_bytes = stages * stage_bytes + 1024 + kEpiWarps * (size_t)kStageBytesPerWarp;
-  bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM);
-  if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM);
-  ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n);
+  bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM, BK) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM, BK);
+  if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM, BK) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM, BK);
+  ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n, BK) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n, BK);
   if (!ok) return QAGNN_ERR_CUDA;
   p.bias = bias;
   p.act = (int)act;
@@ -468,9 +477,11 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.ldp = out.ldp;
   static size_t attr = 0;
   if (smem_bytes > attr) {
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+#define QAGNN_SET_ATTR(A, B) \
+  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
+    QAGNN_SET_ATTR(ACT_NONE, 64); QAGNN_SET_ATTR(ACT_RELU, 64); QAGNN_SET_ATTR(ACT_GELU, 64);
+    QAGNN_SET_ATTR(ACT_NONE, 32); QAGNN_SET_ATTR(ACT_RELU, 32); QAGNN_SET_ATTR(ACT_GELU, 32);
+#undef QAGNN_SET_ATTR
     attr = smem_bytes;
   }
   static int sms = 0;
@@ -481,9 +492,15 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   }
   const long long total_tiles = (long long)n_tiles * ((M + BM - 1) / BM);
   const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);
-  if (act == ACT_NONE) gemm_tc_kernel<ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(p);
-  else if (act == ACT_RELU) gemm_tc_kernel<ACT_RELU><<<grid, kThreads, smem_bytes, st>>>(p);
-  else gemm_tc_kernel<ACT_GELU><<<grid, kThreads, smem_bytes, st>>>(p);
+#define QAGNN_LAUNCH(A)                                                                  \
+  do {                                                                                   \
+    if (BK == 64) gemm_tc_kernel<A, 64><<<grid, kThreads, smem_bytes, st>>>(p);           \
+    else gemm_tc_kernel<A, 32><<<grid, kThreads, smem_bytes, st>>>(p);                    \
+  } while (0)
+  if (act == ACT_NONE) QAGNN_LAUNCH(ACT_NONE);
+  else if (act == ACT_RELU) QAGNN_LAUNCH(ACT_RELU);
+  else QAGNN_LAUNCH(ACT_GELU);
+#undef QAGNN_LAUNCH
   QAGNN_CHECK_LAUNCH();
   return QAGNN_OK;
 }
