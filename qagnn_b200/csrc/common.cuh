@@ -122,6 +122,7 @@ struct TcOperand {
   const void* hi;
   const void* lo;
   int ld, K;
+  int replicas = 1, replica_rows = 0;  // weights only: the planes hold `replicas` copies, `replica_rows` rows apart
 };
 // Any subset of: fp32 row-major C, fp32 head-major padded (projection for the tiled MP), split-bf16 planes.
 struct TcOutput {

@@ -51,6 +51,7 @@ struct alignas(64) TcParams {
   __nv_bfloat16 *c_hi, *c_lo;
   int ldp;
   unsigned tmem_cols;
+  int wrep, wrep_rows;  // W planes replicated wrep times along rows (wrep_rows apart): spreads the hot W lines over L2 slices
   int debug;  // QAGNN_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip TMEM loads, 4 skip MMAs (timing experiments)
 };
 
@@ -192,8 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       long long it = 0;  // k-block counter across tiles
+      const int w_off = (int)(blockIdx.x % (unsigned)p.wrep) * p.wrep_rows;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (int)(tile % n_tiles) * p.n_step;
+        const int n0 = (int)(tile % n_tiles) * p.n_step + w_off;
         const int m0 = (int)((tile / n_tiles) * BM);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = (int)(it % p.stages);
@@ -452,7 +454,7 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.tmem_cols = 512;
   static const int BK = [] {
     const char* e = getenv("QAGNN_TC_BK");
-    return (e && atoi(e) == 64) ? 64 : 32;
+    return (e && atoi(e) == 32) ? 32 : 64;
   }();
   const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
   int stages = (int)((226 * 1024 - 1024 - kEpiWarps * kStageBytesPerWarp) / stage_bytes);
@@ -463,7 +465,10 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   const size_t smem_bytes = stages * stage_bytes + 1024 + kEpiWarps * (size_t)kStageBytesPerWarp;
   bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM, BK) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM, BK);
   if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM, BK) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM, BK);
-  ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n, BK) && make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n, BK);
+  p.wrep = W.replicas > 1 ? W.replicas : 1;
+  p.wrep_rows = W.replica_rows;
+  const long long w_rows = p.wrep > 1 ? (long long)(p.wrep - 1) * p.wrep_rows + N : N;
+  ok = ok && make_map(&p.w_hi, W.hi, w_rows, K1 + K2, W.ld, p.umma_n, BK) && make_map(&p.w_lo, W.lo, w_rows, K1 + K2, W.ld, p.umma_n, BK);
   if (!ok) return QAGNN_ERR_CUDA;
   p.bias = bias;
   p.act = (int)act;
