@@ -305,7 +305,7 @@ def run_b200_arm(args):
         "gpu_launches_note": "kernels of libqagnn_b200.so enqueued by the K steps of the kernel-level pass (the CUDA graph "
                              "of the headline pass replays the same kernel nodes)",
         "ms_per_step_per_kernel_launches": ms_eager / args.steps,
-        "roofline": {"kernel": "message passing (mp_scores_kernel + mp_aggregate_kernel), one GATConvE layer",
+        "roofline": {"kernel": "mp_headtile_kernel (fused logits + per-source softmax + out-degree rescale + per-target sum), one GATConvE layer",
                      "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "avg_launch_ms": mp_avg_ms,
                      "launches_timed": int(mp_cnt),
