@@ -39,6 +39,7 @@ constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
 struct alignas(64) TcParams {
   CUtensorMap a_hi[2], a_lo[2], w_hi, w_lo;
+  CUtensorMap o_f32, o_hm, o_hi, o_lo;  // TMA-store maps of the requested outputs
   int nseg, kseg[2];
   int umma_n, n_step, N, stages;
   long long M;
@@ -142,8 +143,23 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.f + t);
 }
 
-constexpr int kStagePitch = 34;  // floats; even -> float2-aligned rows for the bf16-plane path
-constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;
+// Per-warp epilogue staging tile: 32 rows x 128 B (fp32 x 32 columns, SWIZZLE_128B) or 2 x (32 rows x 64 B)
+// (bf16 hi / lo x 32 columns, SWIZZLE_64B) — written with conflict-free STS.128, drained by one TMA store.
+constexpr int kStageBytesPerWarp = 4096;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int ACT, int BK>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
@@ -250,105 +266,113 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ===================================== epilogue (warps 0..7) =====================================
-    // TMEM -> registers (thread = row) -> bias/activation -> per-warp smem transpose -> coalesced global stores
-    // (lanes = consecutive columns of one row).  Thread-per-row stores ran at ~1 TB/s; see profiles/r1_gemm_tc.md.
+    // TMEM -> registers (thread = row, 32 columns) -> bias/activation -> swizzled per-warp staging tile (STS.128) ->
+    // one cp.async.bulk.tensor store per 32x32 block.  TMA clips rows >= M and columns past the tensor, so there are
+    // no bound checks; the store drains asynchronously while the warp loads the next block from TMEM.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read (warp id % 4)
-    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 1024) + (size_t)warp * (kStageBytesPerWarp / 4);
+    unsigned char* stg = smem + (size_t)p.stages * stage_bytes + 1024 + (size_t)warp * kStageBytesPerWarp;
+    const bool hm_mode = p.c_hm != nullptr;
+    const int DP = hm_mode ? p.hm.DP : 0;
+    const int per_head = hm_mode ? (DP + 31) / 32 : 0;                      // 32-column blocks per head slab
+    const int nblk = hm_mode ? p.hm.H * per_head : (p.n_step + 31) / 32;    // blocks per tile
     int ti = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
-      const int n0 = (int)(tile % n_tiles) * p.n_step;
-      const long long row0 = (tile / n_tiles) * BM + quad * 32;  // first row of this warp
-      const int n_end = min(n0 + p.n_step, p.N);
+      const int n_tile = (int)(tile % n_tiles);
+      const int n0 = n_tile * p.n_step;
+      const int row0 = (int)((tile / n_tiles) * BM) + quad * 32;  // first row of this warp
       mbar_wait(&acc_full[acc], (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
-      for (int c0 = (warp >> 2) * 32; c0 < p.umma_n && n0 + c0 < n_end; c0 += 32 * (kEpiWarps / 4)) {
-        const int ncol = min(32, p.umma_n - c0);  // 32 or 16 (umma_n is a multiple of 16)
+      for (int blk = warp >> 2; blk < nblk; blk += kEpiWarps / 4) {
+        // accumulator column of the block, and where it lands in the output
+        int tcol, oc0, oslab = 0;
+        if (hm_mode) {
+          const int hh = blk / per_head, q = blk % per_head;
+          tcol = hh * DP + 32 * q;
+          oc0 = 32 * q;
+          oslab = n_tile * p.hm.H + hh;  // one `which` (Q / Kx / Mx) per n tile
+        } else {
+          tcol = 32 * blk;
+          oc0 = n0 + tcol;
+          if (oc0 >= p.N) break;
+        }
         float v[32];
         if (p.debug & 2) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        } else if (ncol == 32) {
-          tmem_ld32(taddr + (uint32_t)c0, v);
         } else {
-          float t[16];
-          tmem_ld16(taddr + (uint32_t)c0, t);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { v[i] = t[i]; v[i + 16] = 0.f; }
+          tmem_ld32(taddr + (uint32_t)tcol, v);
         }
         if (p.debug & 1) continue;
-        const int col0 = n0 + c0;
-        // stage (thread = row): bias + activation, then write the row into the transpose buffer
-        if (p.bias != nullptr) {
-          if (col0 + 32 <= n_end) {  // bias is a 256-byte-aligned blob slice; col0 is a multiple of 16
+        if (p.bias != nullptr) {  // bias is indexed by GEMM column (padded like the weight rows)
+          if (n0 + tcol + 32 <= p.N) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + tcol);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (col0 + i < n_end) v[i] += __ldg(p.bias + col0 + i);
+              if (n0 + tcol + i < p.N) v[i] += __ldg(p.bias + n0 + tcol + i);
           }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float x = v[i];
-          if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
-          if (ACT == ACT_GELU) x = gelu_tanh_fast(x);
-          stg[lane * kStagePitch + i] = x;
+          if (ACT == ACT_RELU) v[i] = fmaxf(v[i], 0.f);
+          if (ACT == ACT_GELU) v[i] = gelu_tanh_fast(v[i]);
         }
-        __syncwarp();
-        const int col = col0 + lane;
-        const bool full_rows = row0 + 32 <= p.M;  // warp-uniform: no per-row bound checks on the common path
-        if (p.c_f32 != nullptr && lane < ncol && col < n_end) {
-          float* dst = p.c_f32 + row0 * p.ldc + col;
-          if (full_rows) {
+        if (p.c_f32 != nullptr || hm_mode) {
+          tma_store_wait_read();  // the previous store has finished reading the staging tile
+          __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 32; ++r) dst[(size_t)r * p.ldc] = stg[r * kStagePitch + lane];
-          } else {
-            for (int r = 0; row0 + r < p.M; ++r) dst[(size_t)r * p.ldc] = stg[r * kStagePitch + lane];
-          }
-        }
-        if (p.c_hm != nullptr && lane < ncol && col < n_end) {
-          // padded head-major output: weight rows are laid out [3][H][DP], so column c = slab*DP + j
-          const int DP = p.hm.DP;
-          float* dst = p.c_hm + ((size_t)(col / DP) * p.M + row0) * DP + (col % DP);
-          if (full_rows) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) dst[r * DP] = stg[r * kStagePitch + lane];
-          } else {
-            for (int r = 0; row0 + r < p.M; ++r) dst[r * DP] = stg[r * kStagePitch + lane];
+          for (int c = 0; c < 8; ++c)  // row = lane, 16-byte chunk c -> chunk c ^ (row & 7)  (SWIZZLE_128B)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (hm_mode) tma_store_3d(&p.o_hm, oc0, row0, oslab, stg);
+            else tma_store_2d(&p.o_f32, oc0, row0, stg);
+            tma_store_commit();
           }
         }
         if (p.c_hi != nullptr) {
-          // two rows per instruction: lanes 0-15 -> row 2q, lanes 16-31 -> row 2q+1, two columns per lane
-          const int j2 = 2 * (lane & 15);
-          if (j2 < ncol && col0 + j2 < n_end) {
-#pragma unroll 4
-            for (int q = 0; q < 16; ++q) {
-              const int r = 2 * q + (lane >> 4);
-              if (row0 + r >= p.M) continue;
-              const float2 x = *reinterpret_cast<const float2*>(stg + r * kStagePitch + j2);
-              __nv_bfloat162 hh, ll;
-              hh.x = __float2bfloat16_rn(x.x);
-              hh.y = __float2bfloat16_rn(x.y);
-              ll.x = __float2bfloat16_rn(x.x - __bfloat162float(hh.x));
-              ll.y = __float2bfloat16_rn(x.y - __bfloat162float(hh.y));
-              *reinterpret_cast<__nv_bfloat162*>(p.c_hi + (row0 + r) * p.ldp + col0 + j2) = hh;
-              *reinterpret_cast<__nv_bfloat162*>(p.c_lo + (row0 + r) * p.ldp + col0 + j2) = ll;
-            }
+          tma_store_wait_read();
+          __syncwarp();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 h2, l2;
+            h2.x = __float2bfloat16_rn(v[2 * i]);
+            h2.y = __float2bfloat16_rn(v[2 * i + 1]);
+            l2.x = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h2.x));
+            l2.y = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h2.y));
+            hi[i] = *reinterpret_cast<uint32_t*>(&h2);
+            lo[i] = *reinterpret_cast<uint32_t*>(&l2);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // rows of 64 B: chunk c -> c ^ ((row >> 1) & 3)  (SWIZZLE_64B)
+            const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(stg + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<uint4*>(stg + 2048 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.o_hi, oc0, row0, stg);
+            tma_store_2d(&p.o_lo, oc0, row0, stg + 2048);
+            tma_store_commit();
           }
         }
-        __syncwarp();
       }
       // accumulator drained: hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
     }
+    tma_store_wait_all();  // global writes of this warp's stores are complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -405,6 +429,21 @@ bool make_map(CUtensorMap* m, const void* base, long long rows, int K, int ld, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// output tensor: dims {cols, rows[, slabs]}, box {32, 32[, 1]}; fp32 -> SWIZZLE_128B, bf16 -> SWIZZLE_64B
+bool make_out_map(CUtensorMap* m, void* base, int elem_bytes, long long cols, long long rows, long long slabs,
+                  size_t row_stride_bytes, size_t slab_stride_bytes) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(slabs > 0 ? slabs : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_bytes, (cuuint64_t)slab_stride_bytes};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int rank = slabs > 0 ? 3 : 2;
+  return enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool gemm_tc_available() {
@@ -439,7 +478,7 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   memset(&p, 0, sizeof(p));
   int n_tiles = (N + 223) / 224;  // UMMA_N <= 224 leaves room for two stages + the epilogue staging buffers
   p.n_step = (N + n_tiles - 1) / n_tiles;
-  p.n_step = (p.n_step + 7) / 8 * 8;
+  p.n_step = (p.n_step + 31) / 32 * 32;  // whole 32-column store blocks: neighbouring tiles never overlap
   if (out.hm_buf != nullptr) {  // one `which` (Q / Kx / Mx) per tile: H*DP padded columns
     p.n_step = out.hm.H * out.hm.DP;
     if (p.n_step > 256 || p.n_step % 16 != 0 || N % p.n_step != 0) return QAGNN_ERR_UNSUPPORTED;
@@ -469,7 +508,16 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.wrep_rows = W.replica_rows;
   const long long w_rows = p.wrep > 1 ? (long long)(p.wrep - 1) * p.wrep_rows + N : N;
   ok = ok && make_map(&p.w_hi, W.hi, w_rows, K1 + K2, W.ld, p.umma_n, BK) && make_map(&p.w_lo, W.lo, w_rows, K1 + K2, W.ld, p.umma_n, BK);
+  // output maps (TMA stores): fp32 boxes of 32 columns x 32 rows (128-byte swizzle), bf16 boxes 32 x 32 (64-byte swizzle)
+  if (out.f32 != nullptr) ok = ok && make_out_map(&p.o_f32, out.f32, 4, N, M, 0, (size_t)out.ldc * 4, 0);
+  if (out.hm_buf != nullptr)
+    ok = ok && make_out_map(&p.o_hm, out.hm_buf, 4, out.hm.DP, M, N / p.n_step * out.hm.H, (size_t)out.hm.DP * 4,
+                            (size_t)M * out.hm.DP * 4);
+  if (out.hi != nullptr)
+    ok = ok && make_out_map(&p.o_hi, out.hi, 2, N, M, 0, (size_t)out.ldp * 2, 0) &&
+         make_out_map(&p.o_lo, out.lo, 2, N, M, 0, (size_t)out.ldp * 2, 0);
   if (!ok) return QAGNN_ERR_CUDA;
+  if ((out.f32 && (out.ldc % 4 != 0)) || (out.hi && (out.ldp % 8 != 0))) return QAGNN_ERR_UNSUPPORTED;
   p.bias = bias;
   p.act = (int)act;
   { const char* e = getenv("QAGNN_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
