@@ -245,12 +245,11 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
           const float4* k1 = kt + (w1 >> 16) * NCH;
           const float4* e1 = tab + (w1 & 0xffffu) * NCH;
           float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-          const bool on0 = i0 + j < deg, on1 = i0 + j + 1 < deg;  // quarter-warps past their degree skip the LDS
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
-            const float4 x0 = on0 ? k0[chunk[k]] : z4, y0 = on0 ? e0[chunk[k]] : z4;
-            const float4 x1 = on1 ? k1[chunk[k]] : z4, y1 = on1 ? e1[chunk[k]] : z4;
+            // (quarter-warps past their node's degree read row 0 against a discarded result; predicating these loads
+            //  off saves shared-memory wavefronts but cost 143 -> 177 us in issue slots: measured, reverted)
+            const float4 x0 = k0[chunk[k]], y0 = e0[chunk[k]], x1 = k1[chunk[k]], y1 = e1[chunk[k]];
             a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[u][k]), a0);
             a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[u][k]), a0);
             a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[u][k]), a1);
@@ -355,12 +354,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
           const float4* m1 = mt + (w1 >> 16) * NCH;
           const float4* e1 = tab + (w1 & 0xffffu) * NCH;
           const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
-          const bool on0 = i0 + j < deg, on1 = i0 + j + 1 < deg;
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < CPL; ++k) {
-            const float4 x0 = on0 ? m0[chunk[k]] : z4, y0 = on0 ? e0[chunk[k]] : z4;
-            const float4 x1 = on1 ? m1[chunk[k]] : z4, y1 = on1 ? e1[chunk[k]] : z4;
+            const float4 x0 = m0[chunk[k]], y0 = e0[chunk[k]], x1 = m1[chunk[k]], y1 = e1[chunk[k]];
             acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
             acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
             acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
