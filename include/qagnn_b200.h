@@ -116,6 +116,8 @@ typedef struct qagnn_prep_layout {
   size_t pk_src;       /* [E'] (tgt - graph_base) << 16 | combo, by-source order (n_per_graph > 0 only) */
   size_t pk_tgt;       /* [E'] (src - graph_base) << 16 | combo, by-target order (n_per_graph > 0 only) */
   size_t csr_src_tpos; /* [E'] position of edge perm_src[p] in the by-target order       */
+  size_t order_src;    /* [N]  per sub-graph: local node ids sorted by out-degree, descending (n_per_graph > 0) */
+  size_t order_tgt;    /* [N]  same by in-degree: the tiled kernel gives each warp 4 nodes of similar degree   */
   size_t status;       /* [4]  device-side error word + counters                        */
   size_t scratch;      /* internal                                                     */
 } qagnn_prep_layout;

@@ -41,7 +41,7 @@ class MPParams(C.Structure):
 class PrepLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total_bytes", "src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src",
                                           "perm_tgt", "csr_src_tgt", "csr_src_combo", "csr_tgt_src", "csr_tgt_combo",
-                                          "csr_tgt_apos", "pk_src", "pk_tgt", "csr_src_tpos", "status", "scratch")]
+                                          "csr_tgt_apos", "pk_src", "pk_tgt", "csr_src_tpos", "order_src", "order_tgt", "status", "scratch")]
 
 
 EXPORTS = {

@@ -234,6 +234,31 @@ __global__ void prep_tpos_kernel(int64_t Ep, const int32_t* __restrict__ perm_sr
     csr_src_tpos[p] = inv_tgt[perm_src[p]];
 }
 
+// Per sub-graph (one CTA each, blockIdx.y = direction): local node ids ordered by degree, descending, so that the
+// 4 nodes a warp of the tiled kernel walks together have (nearly) the same number of edges.  Ties are broken by a
+// shared-memory atomic counter: the order only schedules work, it never changes a summation order.
+__global__ void __launch_bounds__(256) prep_degree_order_kernel(int npg, const int32_t* __restrict__ rowptr_src,
+                                                                const int32_t* __restrict__ rowptr_tgt,
+                                                                int32_t* __restrict__ order_src, int32_t* __restrict__ order_tgt) {
+  __shared__ int hist[256], base[256];
+  const int32_t* rowptr = blockIdx.y ? rowptr_tgt : rowptr_src;
+  int32_t* order = (blockIdx.y ? order_tgt : order_src) + (size_t)blockIdx.x * npg;
+  const int64_t v0 = (int64_t)blockIdx.x * npg;
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < npg; i += 256) atomicAdd(&hist[min(rowptr[v0 + i + 1] - rowptr[v0 + i], 255)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 255; b >= 0; --b) { base[b] = run; run += hist[b]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npg; i += 256) {
+    const int b = min(rowptr[v0 + i + 1] - rowptr[v0 + i], 255);
+    order[atomicAdd(&base[b], 1)] = i;
+  }
+}
+
 inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -266,6 +291,8 @@ extern "C" int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layo
   out->pk_src = take(Ep);
   out->pk_tgt = take(Ep);
   out->csr_src_tpos = take(Ep);
+  out->order_src = take(N);
+  out->order_tgt = take(N);
   out->status = take(4);
   out->scratch = o;
   o += make_scratch(N, E).total * 4;
@@ -335,6 +362,11 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   QAGNN_CHECK_LAUNCH();
   prep_tpos_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_src), scr + sc.inv_tgt, I(pl.csr_src_tpos));
   QAGNN_CHECK_LAUNCH();
+  if (npg > 0) {
+    prep_degree_order_kernel<<<dim3((unsigned)(N / npg), 2), 256, 0, st>>>(npg, I(pl.rowptr_src), I(pl.rowptr_tgt),
+                                                                          I(pl.order_src), I(pl.order_tgt));
+    QAGNN_CHECK_LAUNCH();
+  }
   if (validate) {
     int32_t h = 0;
     QAGNN_CHECK_CUDA(cudaMemcpyAsync(&h, I(pl.status), 4, cudaMemcpyDeviceToHost, st));

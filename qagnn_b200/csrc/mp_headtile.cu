@@ -31,7 +31,7 @@ namespace {
 struct HeadTileParams {
   int64_t N, Eps;  // Eps = per-head stride of score/alpha (E' rounded up to 4)
   int n, G, H, D, d, DP, C, S, W, ecap;
-  const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *pk_tgt, *tpos, *perm_src;
+  const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *pk_tgt, *tpos, *perm_src, *order_src, *order_tgt;
   const float *qkmh, *keh, *meh;
   float *score, *alpha, *aggr, *alpha_out;
   void *aggr_hi, *aggr_lo;  // optional split-bf16 planes of aggr [N, D] (A operand of the node-MLP GEMM)
@@ -78,7 +78,7 @@ __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z,
 
 // shared-memory carve-up (bytes from the start of dynamic smem)
 struct SmemMap {
-  uint32_t tab, tile0, tile_bytes, rp0, rp_bytes, ia0, ib0, idx_bytes, bars, meta;
+  uint32_t tab, tile0, tile_bytes, rp0, rp_bytes, od0, od_bytes, ia0, ib0, idx_bytes, bars, meta;
 };
 __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap) {
   SmemMap m;
@@ -87,7 +87,9 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap)
   m.tile_bytes = (uint32_t)n * DP * 4;
   m.rp0 = m.tile0 + 2 * m.tile_bytes;
   m.rp_bytes = (uint32_t)((n + 1 + 3 + 3) / 4 * 4) * 4;  // + alignment slack of the slice start
-  m.ia0 = m.rp0 + 2 * m.rp_bytes;
+  m.od0 = m.rp0 + 2 * m.rp_bytes;
+  m.od_bytes = (uint32_t)((n + 3 + 3) / 4 * 4) * 4;  // degree-sorted local node ids (+ alignment slack)
+  m.ia0 = m.od0 + 2 * m.od_bytes;
   m.idx_bytes = (uint32_t)ecap * 4;
   m.ib0 = m.ia0 + 2 * m.idx_bytes;
   m.bars = m.ib0 + 2 * m.idx_bytes;
@@ -152,13 +154,15 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
       const uint32_t idx_bytes = staged ? (uint32_t)((cnt + 3) & ~3) * 4u : 0u;
       const int64_t rp_base = v0 & ~(int64_t)3;
       const uint32_t rp_bytes = (uint32_t)(((v0 - rp_base) + p.n + 1 + 3) & ~3) * 4u;
-      mbar_expect_tx(&full[b], sm.tile_bytes + rp_bytes + 2 * idx_bytes);
+      mbar_expect_tx(&full[b], sm.tile_bytes + rp_bytes + (uint32_t)(((v0 - rp_base) + p.n + 3) & ~3) * 4u + 2 * idx_bytes);
       {
         const char* src = (const char*)((ph2 ? Mh : Kh) + (size_t)v0 * p.DP);
         char* dst = (char*)(smem_raw + sm.tile0 + b * sm.tile_bytes);
         for (uint32_t o = 0; o < sm.tile_bytes; o += 32768) bulk_g2s(dst + o, src + o, min(32768u, sm.tile_bytes - o), &full[b]);
       }
       bulk_g2s(smem_raw + sm.rp0 + b * sm.rp_bytes, rowptr + rp_base, rp_bytes, &full[b]);
+      const uint32_t od_bytes = (uint32_t)(((v0 - rp_base) + p.n + 3) & ~3) * 4u;
+      bulk_g2s(smem_raw + sm.od0 + b * sm.od_bytes, (ph2 ? p.order_tgt : p.order_src) + rp_base, od_bytes, &full[b]);
       if (staged && idx_bytes) {
         bulk_g2s(smem_raw + sm.ia0 + b * sm.idx_bytes, (ph2 ? p.pk_tgt : p.pk_src) + base, idx_bytes, &full[b]);
         if (ph2) bulk_g2s(smem_raw + sm.ib0 + b * sm.idx_bytes, p.alpha + hE + base, idx_bytes, &full[b]);
@@ -190,8 +194,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
   const float4* tab = reinterpret_cast<const float4*>(smem_raw + sm.tab);
 
   auto load_q = [&](int g, int quad, float4 (&q)[CPL]) {
-    const int vl = quad * 4 + qi;
-    const int64_t v = (int64_t)g * p.n + (vl < p.n ? vl : 0);
+    const int slot_i = quad * 4 + qi;  // position in the degree-sorted order of graph g
+    const int vl = p.order_src[(int64_t)g * p.n + (slot_i < p.n ? slot_i : 0)];
+    const int64_t v = (int64_t)g * p.n + vl;
 #pragma unroll
     for (int k = 0; k < CPL; ++k)
       q[k] = (cvalid[k] && quad < nquads) ? __ldg(reinterpret_cast<const float4*>(Qh + v * p.DP) + chunk[k])
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     mbar_wait(&full[b], (t >> 1) & 1);
     const float4* kt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
     const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
+    const int* od = reinterpret_cast<const int*>(smem_raw + sm.od0 + b * sm.od_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
     const int* ib = reinterpret_cast<const int*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
     const int base = rp[0] & ~3;
@@ -226,9 +232,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     for (int u = 0; u < QPW; ++u) {
       const int quad = warp + u * p.W;
       if (quad >= nquads) break;
-      const int vl = quad * 4 + qi;
-      const bool nvalid = vl < p.n;
-      const int begr = rp[nvalid ? vl : 0] - base;
+      const bool nvalid = quad * 4 + qi < p.n;
+      const int vl = nvalid ? od[quad * 4 + qi] : 0;  // 4 nodes of similar out-degree per warp
+      const int begr = rp[vl] - base;
       const int deg = nvalid ? rp[vl + 1] - base - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     mbar_wait(&full[b], (t >> 1) & 1);
     const float4* mt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
     const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
+    const int* od = reinterpret_cast<const int*>(smem_raw + sm.od0 + b * sm.od_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* ia = reinterpret_cast<const int*>(smem_raw + sm.ia0 + b * sm.idx_bytes);
     const float* ib = reinterpret_cast<const float*>(smem_raw + sm.ib0 + b * sm.idx_bytes);
     const int base = rp[0] & ~3;
@@ -327,9 +334,9 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     for (int u = 0; u < QPW; ++u) {
       const int quad = warp + u * p.W;
       if (quad >= nquads) break;
-      const int vl = quad * 4 + qi;
-      const bool nvalid = vl < p.n;
-      const int begr = rp[nvalid ? vl : 0] - base;
+      const bool nvalid = quad * 4 + qi < p.n;
+      const int vl = nvalid ? od[quad * 4 + qi] : 0;  // 4 nodes of similar in-degree per warp
+      const int begr = rp[vl] - base;
       const int deg = nvalid ? rp[vl + 1] - base - begr : 0;
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
@@ -498,7 +505,7 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   p.n = s.n_per_graph; p.G = (int)(s.N / s.n_per_graph); p.H = s.H; p.D = s.D; p.d = s.D / s.H; p.DP = plan.DP;
   p.C = plan.C; p.S = plan.S; p.W = plan.W; p.ecap = plan.ecap;
   p.rowptr_src = I(L.rowptr_src); p.rowptr_tgt = I(L.rowptr_tgt); p.pk_src = I(L.pk_src); p.pk_tgt = I(L.pk_tgt);
-  p.tpos = I(L.csr_src_tpos); p.perm_src = I(L.perm_src);
+  p.tpos = I(L.csr_src_tpos); p.perm_src = I(L.perm_src); p.order_src = I(L.order_src); p.order_tgt = I(L.order_tgt);
   p.qkmh = qkmh; p.keh = keh; p.meh = meh; p.score = score; p.alpha = alpha; p.aggr = aggr; p.alpha_out = alpha_out;
   p.aggr_hi = (s.D % 2 == 0 && (s.D / s.H) % 2 == 0) ? aggr_hi : nullptr; p.aggr_lo = aggr_lo;
   if (aggr_hi != nullptr && p.aggr_hi == nullptr) return QAGNN_ERR_UNSUPPORTED;

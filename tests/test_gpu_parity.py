@@ -48,6 +48,15 @@ def test_graph_prep_bit_exact(name):
     assert np.array_equal(got["pk_src"], ((ref["tgt"] % n) << 16 | ref["combo"])[ref["perm_src"]])
     assert np.array_equal(got["pk_tgt"], ((ref["src"] % n) << 16 | ref["combo"])[ref["perm_tgt"]])
     assert torch.equal(prep.edge_index_prime().cpu(), fx["edge_index_prime"])
+    # degree-sorted schedule of the tiled kernel: a permutation of each graph's nodes, degrees non-increasing
+    N = inp["node_type"].numel()
+    for name_o, deg in (("order_src", ref["outdeg"]), ("order_tgt", ref["indeg"])):
+        order = prep.buf[getattr(prep.layout, name_o):getattr(prep.layout, name_o) + 4 * N].view(torch.int32).cpu().numpy()
+        for g in range(N // n):
+            o = order[g * n:(g + 1) * n]
+            assert sorted(o.tolist()) == list(range(n)), name_o
+            dg = np.minimum(deg[g * n + o], 255)
+            assert (np.diff(dg) <= 0).all(), name_o
 
 
 @pytest.mark.parametrize("name", Hh.golden_names("mp"))
