@@ -21,6 +21,8 @@
 // Node rows come from the head-major padded projection layout [3][H][N][DP] written by the
 // projection GEMM, so a tile is one contiguous n*DP*4-byte bulk copy.
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,6 +37,7 @@ struct HeadTileParams {
   const float *qkmh, *keh, *meh;
   float *score, *alpha, *aggr, *alpha_out;
   void *aggr_hi, *aggr_lo;  // optional split-bf16 planes of aggr [N, D] (A operand of the node-MLP GEMM)
+  unsigned long long* trace;  // optional [4]: consumer-warp cycles {total, waiting for tiles, waiting for tables, warps}
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,11 +206,17 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
   };
 
+  long long t_begin = 0, t_wait_tile = 0, t_wait_tab = 0;
+  if (p.trace != nullptr) t_begin = clock64();
   // ---------------------------------- phase 1: attention weights ----------------------------------
   float4 qn[QPW][CPL];  // Q rows of this warp's quads, prefetched one graph ahead
 #pragma unroll
   for (int u = 0; u < QPW; ++u) load_q(slot, warp + u * p.W, qn[u]);
-  mbar_wait(tabbar, 0);
+  {
+    const long long c0 = p.trace ? clock64() : 0;
+    mbar_wait(tabbar, 0);
+    if (p.trace) t_wait_tab += clock64() - c0;
+  }
   for (int t = 0; t < Gc; ++t) {
     const int b = t & 1;
     const int g = slot + t * p.S;
@@ -220,7 +229,11 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
 #pragma unroll
       for (int u = 0; u < QPW; ++u) load_q(g + p.S, warp + u * p.W, qn[u]);
     }
-    mbar_wait(&full[b], (t >> 1) & 1);
+    {
+      const long long c0 = p.trace ? clock64() : 0;
+      mbar_wait(&full[b], (t >> 1) & 1);
+      if (p.trace) t_wait_tile += clock64() - c0;
+    }
     const float4* kt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
     const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* od = reinterpret_cast<const int*>(smem_raw + sm.od0 + b * sm.od_bytes) + (int)(((int64_t)g * p.n) & 3);
@@ -318,11 +331,19 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
   }
 
   // ---------------------------------- phase 2: weighted sum by target ----------------------------------
-  mbar_wait(tabbar, 1);
+  {
+    const long long c0 = p.trace ? clock64() : 0;
+    mbar_wait(tabbar, 1);
+    if (p.trace) t_wait_tab += clock64() - c0;
+  }
   for (int t = Gc; t < 2 * Gc; ++t) {
     const int b = t & 1;
     const int g = slot + (t - Gc) * p.S;
-    mbar_wait(&full[b], (t >> 1) & 1);
+    {
+      const long long c0 = p.trace ? clock64() : 0;
+      mbar_wait(&full[b], (t >> 1) & 1);
+      if (p.trace) t_wait_tile += clock64() - c0;
+    }
     const float4* mt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
     const int* rp = reinterpret_cast<const int*>(smem_raw + sm.rp0 + b * sm.rp_bytes) + (int)(((int64_t)g * p.n) & 3);
     const int* od = reinterpret_cast<const int*>(smem_raw + sm.od0 + b * sm.od_bytes) + (int)(((int64_t)g * p.n) & 3);
@@ -412,6 +433,12 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
+  }
+  if (p.trace != nullptr && lane == 0) {
+    atomicAdd(p.trace + 0, (unsigned long long)(clock64() - t_begin));
+    atomicAdd(p.trace + 1, (unsigned long long)t_wait_tile);
+    atomicAdd(p.trace + 2, (unsigned long long)t_wait_tab);
+    atomicAdd(p.trace + 3, 1ull);
   }
 }
 
@@ -510,6 +537,26 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   p.aggr_hi = (s.D % 2 == 0 && (s.D / s.H) % 2 == 0) ? aggr_hi : nullptr; p.aggr_lo = aggr_lo;
   if (aggr_hi != nullptr && p.aggr_hi == nullptr) return QAGNN_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)(plan.S * s.H), block = (unsigned)(plan.W + 1) * 32;
+  // QAGNN_MP_TRACE=1: cycle accounting of the consumer warps (diagnostic; synchronises after every launch)
+  static const bool trace_on = [] { const char* e = getenv("QAGNN_MP_TRACE"); return e && atoi(e) != 0; }();
+  static unsigned long long* trace_buf = nullptr;
+  p.trace = nullptr;
+  if (trace_on) {
+    if (!trace_buf) QAGNN_CHECK_CUDA(cudaMalloc(&trace_buf, 4 * sizeof(unsigned long long)));
+    QAGNN_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, 4 * sizeof(unsigned long long), st));
+    p.trace = trace_buf;
+  }
+  struct TraceDump {
+    bool on; unsigned long long* buf; cudaStream_t st;
+    ~TraceDump() {
+      if (!on) return;
+      unsigned long long h[4];
+      cudaMemcpyAsync(h, buf, sizeof(h), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      if (h[3]) fprintf(stderr, "[qagnn mp trace] consumer warps %llu: avg cycles %.0f, waiting for tiles %.1f %%, for tables %.1f %%\n",
+                        h[3], (double)h[0] / h[3], 100.0 * h[1] / h[0], 100.0 * h[2] / h[0]);
+    }
+  } dump{trace_on, trace_buf, st};
   if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1>(p, plan, grid, block, st);
   if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2>(p, plan, grid, block, st);
   if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1>(p, plan, grid, block, st);
