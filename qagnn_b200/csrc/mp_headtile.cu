@@ -190,9 +190,11 @@ __global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(c
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     cvalid[k] = (l8 + 8 * k) < NCH;
-    // idle lanes re-read their own first chunk against q = 0: finite data, and (unlike chunk 0) bytes
-    // 16*l8.. do not share banks with chunks 8.. that the active lanes of the quarter-warp read
-    chunk[k] = cvalid[k] ? l8 + 8 * k : l8;
+    // idle lanes (chunk slot past the row) re-read an in-row chunk against q = 0, so the product is 0 * finite.
+    // It must stay INSIDE the row: the bytes after a row's last chunk belong to the next row / the next smem region
+    // and 0 * NaN would poison the shuffled sum (found with compute-sanitizer, whose smem fill is not finite).
+    // For CPL == 2 the slot is l8 + 8 >= NCH > 8, so l8 % NCH == l8: bytes 16*l8.. do not share banks with chunks 8..
+    chunk[k] = cvalid[k] ? l8 + 8 * k : l8 % NCH;
   }
   const float4* tab = reinterpret_cast<const float4*>(smem_raw + sm.tab);
 
