@@ -310,7 +310,13 @@ def run_b200_arm(args):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "avg_launch_ms": mp_avg_ms,
                      "launches_timed": int(mp_cnt),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_mp_headtile_ncu.md)
-                     "traffic": 187043328 if world == 1 else None},
+                     "traffic": 191374336 if world == 1 else None},  # 173.0 MB read + 18.3 MB written
+        # second-largest kernel: the tcgen05 projection GEMM [N,2D]x[2D,3D], three bf16 passes (hi*hi, hi*lo, lo*hi)
+        "roofline_gemm": (lambda ms_: {"kernel": "gemm_tc_kernel (projection Q|Kx|Mx)", "bound": "tensor",
+                                       "achieved": 3 * 2 * N * 2 * D * 3 * D / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0,
+                                       "peak": peaks.get("bf16_tflops", 1590.0), "unit": "TFLOP/s",
+                                       "frac": (3 * 2 * N * 2 * D * 3 * D / (ms_ * 1e-3) / 1e12) / peaks.get("bf16_tflops", 1590.0) if ms_ > 0 else 0.0,
+                                       "avg_launch_ms": ms_})(prof["projection"][0] / max(prof["projection"][1], 1)),
         "stages": stages,
         "clocks": clocks,
     }

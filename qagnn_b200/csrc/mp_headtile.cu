@@ -101,8 +101,8 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap)
 }
 inline size_t smem_total(const SmemMap& m) { return (size_t)m.meta + 4 * 4 + 16; }
 
-template <int CPL, int QPW>  // float4 chunks per lane; node-quads per consumer warp and graph (1 or 2)
-__global__ void __launch_bounds__(QPW == 2 ? 832 : 1024, 1) mp_headtile_kernel(const HeadTileParams p) {
+template <int CPL, int QPW>  // float4 chunks per lane; node-quads per consumer warp and graph (1..4)
+__global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 576 : 448, 1) mp_headtile_kernel(const HeadTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NCH = p.DP / 4;
   const SmemMap sm = make_smem_map(p.C, p.DP, p.n, p.ecap);
@@ -485,11 +485,14 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   pl.smem = smem_total(make_smem_map(pl.C, pl.DP, s.n_per_graph, pl.ecap));
   pl.S = sms / s.H;
   const int quads = (s.n_per_graph + 3) / 4;
-  const int passes = (quads + 30) / 31;  // at most 31 consumer warps + 1 loader warp
+  int passes = (quads + 30) / 31;  // at most 31 consumer warps + 1 loader warp
   if (passes > 2) return pl;
+  static const int forced_qpw = [] { const char* e = getenv("QAGNN_MP_QPW"); return e ? atoi(e) : 0; }();
+  if (forced_qpw >= passes && forced_qpw <= 4) passes = forced_qpw;  // fewer, fatter warps (more registers each)
   pl.qpw = passes;
   pl.W = (quads + passes - 1) / passes;
-  if (passes == 2 && pl.W > 25) return pl;  // the 2-quad variant is compiled for <= 26 warps (78 registers)
+  const int max_w = passes == 1 ? 31 : passes == 2 ? 25 : passes == 3 ? 17 : 13;  // launch bounds of the variants
+  if (pl.W > max_w) return pl;
   pl.ok = true;
   return pl;
 }
@@ -561,7 +564,11 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   } dump{trace_on, trace_buf, st};
   if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1>(p, plan, grid, block, st);
   if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 3) return launch_t<1, 3>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 4) return launch_t<1, 4>(p, plan, grid, block, st);
   if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 3) return launch_t<2, 3>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 4) return launch_t<2, 4>(p, plan, grid, block, st);
   return launch_t<2, 2>(p, plan, grid, block, st);
 }
 
