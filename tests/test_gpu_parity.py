@@ -287,3 +287,39 @@ def test_lm_qagnn_forward_api_with_packed_and_nested_adjacency():
                                                inp["node_score"], inp["adj_lengths"], inp["edge_index"], inp["edge_type"],
                                                k, 4, 38, 2, 0)
     Hh.assert_close(logits.view(-1, 1), ref_logits, "LM_QAGNN logits vs oracle decoder")
+
+
+def test_tiled_kernel_hub_nodes_and_unstaged_graphs():
+    """Tiled-path corner cases against the oracle and the CSR kernels: a degree-199 hub (logits beyond the 8th edge go
+    through the L2 scratch), a graph with more edges than the shared-memory CSR staging holds (global fallback inside
+    the kernel), a graph with no edges at all, in one batch."""
+    n, D, k = 200, 200, 1
+    g = torch.Generator().manual_seed(11)
+    def rnd(e, lo=0):
+        return torch.randint(lo, n, (2, e), generator=g)
+    hub = torch.cat([torch.stack([torch.zeros(n - 1, dtype=torch.long), torch.arange(1, n)]),
+                     torch.stack([torch.arange(1, n), torch.zeros(n - 1, dtype=torch.long)])], dim=1)
+    graphs = [rnd(1000), rnd(3600), hub, torch.zeros(2, 0, dtype=torch.long), rnd(900)]
+    ei = torch.cat([e + i * n for i, e in enumerate(graphs)], dim=1)
+    et = torch.randint(0, 38, (ei.size(1),), generator=g)
+    B = len(graphs)
+    nt = torch.randint(0, 3, (B, n), generator=g); nt[:, 0] = 3
+    x = torch.randn(B * n, D, generator=g) * 0.5
+    extra = torch.randn(B * n, D, generator=g) * 0.5
+    sd = O.random_state_dict(k, D, 4, 38, "peaky", seed=11)
+    ref_out, ei2, ref_alpha, ref_aggr = O.gatconve_forward(sd, "gnn_layers.0", x, ei, et, nt.view(-1), extra, 4, 38)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    layer = mod.gnn_layers[0]
+    xd, ed, ntd = x.to(DEV), extra.to(DEV), nt.view(-1).to(DEV)
+    prep_t = GraphPrep(ei.to(DEV), et.to(DEV), ntd, 4, 38, n_per_graph=n)
+    prep_c = GraphPrep(ei.to(DEV), et.to(DEV), ntd, 4, 38, n_per_graph=0)
+    (out_t, (_, al_t)), ag_t = layer(xd, None, None, ntd, ed, return_attention_weights=True, prep=prep_t, return_aggr=True)
+    (out_c, (_, al_c)), ag_c = layer(xd, None, None, ntd, ed, return_attention_weights=True, prep=prep_c, return_aggr=True)
+    Hh.assert_close(al_t, ref_alpha, "alpha tiled vs oracle")
+    Hh.assert_close(al_c, ref_alpha, "alpha csr vs oracle")
+    Hh.assert_close(ag_t, ref_aggr, "aggr tiled vs oracle", atol=1e-4, rtol=2e-4)
+    Hh.assert_close(ag_c, ref_aggr, "aggr csr vs oracle", atol=1e-4, rtol=2e-4)
+    Hh.assert_close(out_t, ref_out, "out tiled vs oracle")
+    Hh.assert_close(out_c, ref_out, "out csr vs oracle")
