@@ -35,6 +35,14 @@ int32_t cuda_fail(cudaError_t e);  // records the error text, returns QAGNN_ERR_
     if (s__ != QAGNN_OK) return s__; \
   } while (0)
 
+// ---- per-device caches (a process may drive several GPUs, e.g. the reference's encoder/decoder split) -------------
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 // ---- optional stage timing (qagnn_profile_*) -------------------------------------------------------
 void prof_begin(int stage, cudaStream_t st);
 void prof_end(int stage, cudaStream_t st);

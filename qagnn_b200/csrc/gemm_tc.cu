@@ -528,7 +528,9 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.c_hi = (__nv_bfloat16*)out.hi;
   p.c_lo = (__nv_bfloat16*)out.lo;
   p.ldp = out.ldp;
-  static size_t attr = 0;
+  static size_t attr_c[kMaxDevices] = {0};  // the attribute is per device
+  const int dev_i = current_device();
+  size_t& attr = attr_c[dev_i];
   if (smem_bytes > attr) {
 #define QAGNN_SET_ATTR(A, B) \
   QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
@@ -537,12 +539,9 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
 #undef QAGNN_SET_ATTR
     attr = smem_bytes;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    QAGNN_CHECK_CUDA(cudaGetDevice(&dev));
-    QAGNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static int sms_c[kMaxDevices] = {0};
+  if (sms_c[dev_i] == 0) QAGNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms_c[dev_i], cudaDevAttrMultiProcessorCount, dev_i));
+  const int sms = sms_c[dev_i];
   const long long total_tiles = (long long)n_tiles * ((M + BM - 1) / BM);
   const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);
 #define QAGNN_LAUNCH(A)                                                                  \

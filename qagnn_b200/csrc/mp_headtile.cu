@@ -465,13 +465,14 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   pl.C = s.R * s.T * s.T + s.T;
   if (pl.C > 65536 || pl.DP > 64) return pl;
   pl.cpl = pl.DP <= 32 ? 1 : 2;
-  static int sms = 0, max_smem = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return pl;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms_c[kMaxDevices] = {0}, smem_c[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms_c[dev] == 0) {
+    cudaDeviceGetAttribute(&smem_c[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms_c[dev], cudaDevAttrMultiProcessorCount, dev);
   }
+  const int sms = sms_c[dev], max_smem = smem_c[dev];
+  if (sms <= 0) return pl;
   pl.sms = sms;
   if (s.H > sms) return pl;
   // index staging capacity: whatever is left after the table and the two tiles, at least a few edges per node
@@ -499,11 +500,12 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
 
 template <int CPL, int QPW>
 int32_t launch_t(const HeadTileParams& p, const HeadTilePlan& plan, unsigned grid, unsigned block, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (plan.smem > attr_smem) {
+  static size_t attr_smem[kMaxDevices] = {0};  // the attribute is per device
+  const int dev = current_device();
+  if (plan.smem > attr_smem[dev]) {
     QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)plan.smem));
-    attr_smem = plan.smem;
+    attr_smem[dev] = plan.smem;
   }
   mp_headtile_kernel<CPL, QPW><<<grid, block, plan.smem, st>>>(p);
   QAGNN_CHECK_LAUNCH();
