@@ -178,6 +178,14 @@ int32_t qagnn_linear_bf16x3(const float *A1, int32_t lda1, int32_t K1, const flo
                             const float *W, int32_t ldw, const float *bias, float *C, int32_t ldc, int64_t M, int32_t N,
                             int32_t act, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The step after the path: QAGNN's masked multi-head attention pooling of the node representations,
+ * MultiheadAttPoolLayer.forward (utils/layers.py:344-371, called at modeling_qagnn.py:180), eval mode, fused into one
+ * kernel that reads X [B, n, D] once.  qs [B, D] = w_qs(sent_vecs) (computed by the caller), mask uint8 [B, n]
+ * (1 = masked out), wk/wv [D, D] and bk/bv [D] = w_ks / w_vs weights; outputs pooled [B, D], attn [n_head*B, n]. */
+int32_t qagnn_attention_pool(int32_t B, int32_t n, int32_t D, int32_t n_head, const float *X, const float *qs,
+                             const uint8_t *mask, const float *wk, const float *bk, const float *wv, const float *bv,
+                             float *pooled, float *attn, void *stream);
+
 /* Launch counters since load (kernels this library enqueued); for bench.py's gpu_launches. */
 int64_t qagnn_launch_count(void);
 

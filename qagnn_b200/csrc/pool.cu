@@ -1,0 +1,120 @@
+// The step after the hot path: QAGNN's masked multi-head attention pooling over the node
+// representations (utils/layers.py:324-371 MultiheadAttPoolLayer + :276-299 MatrixVectorScaledDotProductAttention,
+// called at modeling/modeling_qagnn.py:180), eval mode.
+//
+//   qs = w_qs(sent) [B, nh*dk];  ks = w_ks(X) [B, n, nh, dk];  vs = w_vs(X) [B, n, nh, dv]
+//   attn[h,b,:] = softmax_i( mask ? -inf : qs[b,h]·ks[b,i,h] / sqrt(dk) );  pooled[b, h*dv:(h+1)*dv] = Σ_i attn·vs[b,i,h]
+//
+// The reference materialises ks and vs with two [B*n, D] x [D, D] GEMMs.  Both projections are linear, so they fold
+// into the query / out of the sum:   qs_h·(W_k,h x_i + b_k,h) = (W_k,hᵀ qs_h)·x_i + qs_h·b_k,h   and
+// Σ_i a_i (W_v,h x_i + b_v,h) = W_v,h (Σ_i a_i x_i) + b_v,h   (Σ_i a_i = 1).  One CTA per graph then reads the
+// graph's [n, D] node tile ONCE: logits for all heads, masked softmax, attention-weighted node sum; the two tiny
+// per-graph matrix-vector products run in the same CTA.  No N-sized GEMM, no ks/vs round trip through HBM.
+#include "common.cuh"
+
+namespace qagnn {
+namespace {
+
+constexpr int kPoolThreads = 256;
+
+// dynamic smem: qk[nh][D] | logit[nh][n] | xs[nh][D] | red[32]
+__global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int D, int nh, const float* __restrict__ X,
+                                                                        const float* __restrict__ qs, const unsigned char* __restrict__ mask,
+                                                                        const float* __restrict__ wk, const float* __restrict__ bk,
+                                                                        const float* __restrict__ wv, const float* __restrict__ bv,
+                                                                        float* __restrict__ pooled, float* __restrict__ attn_out, int B) {
+  extern __shared__ float sm[];
+  float* qk = sm;                  // [nh][D]   W_k,hᵀ qs_h
+  float* logit = qk + nh * D;      // [nh][n]
+  float* xs = logit + nh * n;      // [nh][D]   Σ_i attn_i x_i
+  float* cst = xs + nh * D;        // [nh]      qs_h·b_k,h
+  const int b = blockIdx.x, tid = threadIdx.x, dk = D / nh;
+  const float inv_temp = 1.0f / sqrtf((float)dk);
+  const float* Xb = X + (size_t)b * n * D;
+  // fold the key projection into the query: qk[h][j] = Σ_{r in head h} qs[b, r] * wk[r, j]
+  for (int idx = tid; idx < nh * D; idx += kPoolThreads) {
+    const int h = idx / D, j = idx % D;
+    float acc = 0.f;
+    for (int r = 0; r < dk; ++r) acc = fmaf(qs[(size_t)b * D + h * dk + r], wk[(size_t)(h * dk + r) * D + j], acc);
+    qk[idx] = acc;
+  }
+  if (tid < nh) {
+    float acc = 0.f;
+    for (int r = 0; r < dk; ++r) acc = fmaf(qs[(size_t)b * D + tid * dk + r], bk[tid * dk + r], acc);
+    cst[tid] = acc;
+  }
+  __syncthreads();
+  // logits: one warp per node, lanes over D
+  const int warp = tid >> 5, lane = tid & 31, nwarps = kPoolThreads / 32;
+  for (int i = warp; i < n; i += nwarps) {
+    const bool masked = mask[(size_t)b * n + i] != 0;
+    for (int h = 0; h < nh; ++h) {
+      float acc = 0.f;
+      for (int j = lane; j < D; j += 32) acc = fmaf(qk[h * D + j], Xb[(size_t)i * D + j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) logit[h * n + i] = masked ? -INFINITY : (acc + cst[h]) * inv_temp;
+    }
+  }
+  __syncthreads();
+  // masked softmax per head (one warp per head)
+  for (int h = warp; h < nh; h += nwarps) {
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, logit[h * n + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float e = expf(logit[h * n + i] - m);
+      logit[h * n + i] = e;
+      s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int i = lane; i < n; i += 32) {
+      const float a = logit[h * n + i] / s;
+      logit[h * n + i] = a;
+      attn_out[((size_t)h * B + b) * n + i] = a;  // head-major [nh*B, n] like the reference
+    }
+  }
+  __syncthreads();
+  // attention-weighted node sum: xs[h][j] = Σ_i attn[h][i] * X[i][j]   (threads over j, all heads at once)
+  for (int j = tid; j < D; j += kPoolThreads) {
+    for (int h = 0; h < nh; ++h) {
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc = fmaf(logit[h * n + i], Xb[(size_t)i * D + j], acc);
+      xs[h * D + j] = acc;
+    }
+  }
+  __syncthreads();
+  // value projection of the pooled vector: pooled[b, h*dv + r] = wv[h*dv + r, :]·xs[h] + bv
+  for (int idx = tid; idx < D; idx += kPoolThreads) {
+    const int h = idx / dk;
+    float acc = bv[idx];
+    for (int j = 0; j < D; ++j) acc = fmaf(wv[(size_t)idx * D + j], xs[h * D + j], acc);
+    pooled[(size_t)b * D + idx] = acc;
+  }
+}
+
+}  // namespace
+}  // namespace qagnn
+
+using namespace qagnn;
+
+extern "C" int32_t qagnn_attention_pool(int32_t B, int32_t n, int32_t D, int32_t n_head, const float* X, const float* qs,
+                                        const uint8_t* mask, const float* wk, const float* bk, const float* wv, const float* bv,
+                                        float* pooled, float* attn, void* stream) {
+  if (B <= 0 || n <= 0 || D <= 0 || n_head <= 0 || D % n_head != 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (!X || !qs || !mask || !wk || !bk || !wv || !bv || !pooled || !attn) return QAGNN_ERR_INVALID_ARGUMENT;
+  const size_t smem = ((size_t)2 * n_head * D + (size_t)n_head * n + n_head + 8) * sizeof(float);
+  if (smem > 200 * 1024) return QAGNN_ERR_UNSUPPORTED;
+  static size_t attr[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr[dev]) {
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(attention_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[dev] = smem;
+  }
+  attention_pool_kernel<<<B, kPoolThreads, smem, (cudaStream_t)stream>>>(n, D, n_head, X, qs, mask, wk, bk, wv, bv, pooled, attn, B);
+  QAGNN_CHECK_LAUNCH();
+  return QAGNN_OK;
+}

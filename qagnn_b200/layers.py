@@ -78,6 +78,23 @@ class MultiheadAttPoolLayer(nn.Module):
     def forward(self, q, k, mask=None):
         b, l, _ = k.shape
         nh, dk, dv = self.n_head, self.d_k, self.d_v
+        if (k.is_cuda and not self.training and mask is not None and k.dtype == torch.float32
+                and self.w_ks.weight.shape[0] == k.shape[2]):
+            # fused kernel (one read of k, no ks/vs GEMMs): qagnn_attention_pool
+            from . import _lib
+            lib = _lib.load()
+            qs = self.w_qs(q).contiguous()
+            kc = _lib.f32c(k, "k")
+            m8 = mask.to(torch.uint8).contiguous()
+            pooled = torch.empty(b, nh * dv, dtype=torch.float32, device=k.device)
+            attn = torch.empty(nh * b, l, dtype=torch.float32, device=k.device)
+            with torch.cuda.device(k.device):
+                st = lib.qagnn_attention_pool(b, l, k.shape[2], nh, _lib.ptr(kc), _lib.ptr(qs.detach()), _lib.ptr(m8),
+                                              _lib.ptr(self.w_ks.weight.detach()), _lib.ptr(self.w_ks.bias.detach()),
+                                              _lib.ptr(self.w_vs.weight.detach()), _lib.ptr(self.w_vs.bias.detach()),
+                                              _lib.ptr(pooled), _lib.ptr(attn), _lib.stream_ptr(k.device))
+            _lib.check(st, "qagnn_attention_pool")
+            return pooled, attn
         qs = self.w_qs(q).view(b, nh, dk)
         ks = self.w_ks(k).view(b, l, nh, dk)
         vs = self.w_vs(k).view(b, l, nh, dv)

@@ -323,3 +323,20 @@ def test_tiled_kernel_hub_nodes_and_unstaged_graphs():
     Hh.assert_close(ag_c, ref_aggr, "aggr csr vs oracle", atol=1e-4, rtol=2e-4)
     Hh.assert_close(out_t, ref_out, "out tiled vs oracle")
     Hh.assert_close(out_c, ref_out, "out csr vs oracle")
+
+
+def test_fused_attention_pool_matches_torch_formulation():
+    """qagnn_attention_pool (keys/values folded into the query / out of the sum, one pass over the node tile) against
+    the reference formulation of MultiheadAttPoolLayer evaluated with torch ops on the CPU (utils/layers.py:344-371)."""
+    from qagnn_b200.layers import MultiheadAttPoolLayer
+    torch.manual_seed(3)
+    for (b, n, D, S, nh) in [(7, 200, 200, 1024, 2), (3, 33, 64, 48, 4)]:
+        pool = MultiheadAttPoolLayer(nh, S, D).eval()
+        q, k = torch.randn(b, S), torch.randn(b, n, D) * 0.7
+        mask = torch.rand(b, n) < 0.4
+        mask[:, 0] = False
+        with torch.no_grad():
+            ref_out, ref_attn = pool(q, k, mask)            # CPU: einsum path
+            got_out, got_attn = pool.to(DEV)(q.to(DEV), k.to(DEV), mask.to(DEV))  # CUDA: fused kernel
+        Hh.assert_close(got_attn, ref_attn, "pool attn", atol=2e-6, rtol=1e-4)
+        Hh.assert_close(got_out, ref_out, "pooled", atol=2e-5, rtol=1e-4)
