@@ -320,7 +320,7 @@ def run_b200_arm(args):
         "stages": stages,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N=1 only
         r = cpu_reference_run(3, 1, args.cpu_sample_graphs)
         line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
