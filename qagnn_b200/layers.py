@@ -130,7 +130,21 @@ class CustomizedEmbedding(nn.Module):
 
     def _project(self, e):
         e = e * self.scale
-        return self.activation(self.cpt_transform(e)) if hasattr(self, "cpt_transform") else e
+        if not hasattr(self, "cpt_transform"):
+            return e
+        lin = self.cpt_transform
+        if (e.is_cuda and not self.training and not torch.is_grad_enabled() and e.dtype == torch.float32
+                and lin.in_features % 8 == 0 and lin.out_features >= 8):
+            # GELU(cpt_transform(e)) on the tcgen05 split-bf16 GEMM with the activation fused in the epilogue: the
+            # [B*(n-1), concept_in_dim] x [concept_in_dim, concept_dim] product is the largest dense op outside the GNN
+            from . import ops
+            try:
+                out = ops.linear_bf16x3(e.reshape(-1, lin.in_features), lin.weight, lin.bias, act="gelu")
+                return out.view(*e.shape[:-1], lin.out_features)
+            except Exception as exc:  # tensor-core path not available for this shape/driver: plain PyTorch (same math)
+                if "unsupported" not in str(exc).lower():
+                    raise
+        return self.activation(lin(e))
 
     def forward(self, index, contextualized_emb=None):
         if contextualized_emb is not None:
