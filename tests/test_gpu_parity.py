@@ -127,10 +127,14 @@ def test_decoder_matches_reference_golden(name):
     dec.load_state_dict(fx["state_dict"], strict=True)
     dec = dec.to(DEV)
     d = _dev(inp)
-    logits, pool_attn = dec(sent_vecs.to(DEV), concept_ids.to(DEV), d["node_type"], d["node_score"], d["adj_lengths"],
-                            (d["edge_index"], d["edge_type"]))
-    Hh.assert_close(pool_attn, fx["pool_attn"], "pool_attn")
-    Hh.assert_close(logits, fx["logits"], "logits")
+    args = (sent_vecs.to(DEV), concept_ids.to(DEV), d["node_type"], d["node_score"], d["adj_lengths"],
+            (d["edge_index"], d["edge_type"]))
+    logits, pool_attn = dec(*args)                 # autograd on: plain-PyTorch concept projection
+    with torch.no_grad():
+        logits_ng, pool_attn_ng = dec(*args)       # inference mode: concept projection on the tensor-core GEMM
+    for lg, pa in ((logits, pool_attn), (logits_ng, pool_attn_ng)):
+        Hh.assert_close(pa, fx["pool_attn"], "pool_attn")
+        Hh.assert_close(lg, fx["logits"], "logits")
 
 
 def test_out_of_range_indices_raise():
