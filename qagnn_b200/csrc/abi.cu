@@ -371,7 +371,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
 extern "C" size_t qagnn_linear_workspace_bytes(int64_t M, int32_t N, int32_t K1, int32_t K2) {
   if (M <= 0 || N <= 0 || K1 <= 0 || K2 < 0) return 0;
   const size_t K = (size_t)K1 + K2;
-  return align_up(2 * 2 * ((size_t)M * K + 16 * (size_t)(N + 8) * K) + 8 * 1024);  // room for up to 16 W replicas
+  return align_up(2 * 2 * ((size_t)M * K + (size_t)N * K) + 8 * 1024);
 }
 
 extern "C" int32_t qagnn_linear_bf16x3(const float* A1, int32_t lda1, int32_t K1, const float* A2, int32_t lda2, int32_t K2,
@@ -387,17 +387,11 @@ extern "C" int32_t qagnn_linear_bf16x3(const float* A1, int32_t lda1, int32_t K1
   const int K = K1 + K2;
   void *a1h = take((size_t)M * K1), *a1l = take((size_t)M * K1);
   void *a2h = K2 ? take((size_t)M * K2) : nullptr, *a2l = K2 ? take((size_t)M * K2) : nullptr;
-  const char* e_rep = getenv("QAGNN_TC_WREP");
-  const int rep = e_rep ? (atoi(e_rep) < 1 ? 1 : atoi(e_rep)) : 1;
-  const int rep_rows = (N + 7) / 8 * 8;
-  void *wh = take((size_t)rep * rep_rows * K), *wl = take((size_t)rep * rep_rows * K);
+  void *wh = take((size_t)N * K), *wl = take((size_t)N * K);
   QAGNN_RETURN_IF(split_bf16(A1, lda1, M, K1, a1h, a1l, K1, st));
   if (K2) QAGNN_RETURN_IF(split_bf16(A2, lda2, M, K2, a2h, a2l, K2, st));
-  for (int r = 0; r < rep; ++r)
-    QAGNN_RETURN_IF(split_bf16(Wt, ldw, N, K, (char*)wh + (size_t)r * rep_rows * K * 2, (char*)wl + (size_t)r * rep_rows * K * 2, K, st));
+  QAGNN_RETURN_IF(split_bf16(Wt, ldw, N, K, wh, wl, K, st));
   TcOperand o1{a1h, a1l, K1, K1}, o2{a2h, a2l, K2, K2}, ow{wh, wl, K, K};
-  ow.replicas = rep;
-  ow.replica_rows = rep_rows;
   TcOutput out{};
   out.f32 = C;
   out.ldc = ldc;
