@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/qagnn_b200.h: the forward orchestration of
 // GATConvE (modeling/modeling_qagnn.py:411-484) and QAGNN_Message_Passing (modeling_qagnn.py:53-95).
 #include <atomic>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -93,6 +94,49 @@ __global__ void node_feature_prologue_kernel(int64_t N, int D, int T, const int6
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
     extra[v * D + j] = type_tab[t * Dh + j];
     sinb[i] = sinf(basis[j] * node_score[v]);  // precise sinf: arguments reach ~1e4 * |score|
+  }
+}
+
+// Fused node_feature_extra for D/2 <= 128 (modeling_qagnn.py:62-73,86): one CTA = 64 nodes; emb_score's [D/2, D/2] weight
+// and the CTA's sin-basis tile live in shared memory, so the whole prologue (type-table lookup, sin basis, Linear, GELU)
+// is one launch that writes `extra` as fp32 and/or as the split-bf16 planes the projection GEMM consumes.
+constexpr int kNfNodes = 64;
+__global__ void __launch_bounds__(256) node_feature_fused_kernel(int64_t N, int D, int T, const int64_t* __restrict__ node_type,
+                                                                  const float* __restrict__ node_score,
+                                                                  const float* __restrict__ type_tab, const float* __restrict__ basis,
+                                                                  const float* __restrict__ ws, const float* __restrict__ bs,
+                                                                  float* __restrict__ extra, __nv_bfloat16* __restrict__ ex_hi,
+                                                                  __nv_bfloat16* __restrict__ ex_lo) {
+  extern __shared__ float sm_nf[];
+  const int Dh = D / 2;
+  float* Wt = sm_nf;                      // [Dh][Dh]  Wt[k*Dh + j] = ws[j][k]
+  float* Bv = Wt + (size_t)Dh * Dh;       // [kNfNodes][Dh]
+  const int64_t v0 = (int64_t)blockIdx.x * kNfNodes;
+  for (int i = threadIdx.x; i < Dh * Dh; i += 256) Wt[(i % Dh) * Dh + i / Dh] = ws[i];
+  for (int i = threadIdx.x; i < kNfNodes * Dh; i += 256) {
+    const int64_t v = v0 + i / Dh;
+    Bv[i] = v < N ? sinf(basis[i % Dh] * node_score[v]) : 0.f;  // precise sinf: arguments reach ~1e4 * |score|
+  }
+  __syncthreads();
+  auto put = [&](int64_t v, int col, float x) {
+    if (extra != nullptr) extra[v * D + col] = x;
+    if (ex_hi != nullptr) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      ex_hi[v * D + col] = h;
+      ex_lo[v * D + col] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  };
+  for (int o = threadIdx.x; o < kNfNodes * Dh; o += 256) {
+    const int vi = o / Dh, j = o % Dh;
+    const int64_t v = v0 + vi;
+    if (v >= N) continue;
+    float acc = 0.f;
+    const float* b = Bv + vi * Dh;
+    for (int k = 0; k < Dh; ++k) acc = fmaf(b[k], Wt[k * Dh + j], acc);
+    put(v, Dh + j, gelu_tanh(acc + bs[j]));
+    int64_t t = node_type[v];
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+    put(v, j, type_tab[t * Dh + j]);
   }
 }
 
@@ -213,9 +257,24 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
 }
 
 int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, const int64_t* node_type,
-                      const float* node_score, const float* folded, float* extra, float* ws, cudaStream_t st) {
+                      const float* node_score, const float* folded, float* extra, float* ws, cudaStream_t st,
+                      void* ex_hi = nullptr, void* ex_lo = nullptr) {
   ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   const int D = s.D, Dh = D / 2;
+  if (Dh <= 128) {
+    const size_t smem = ((size_t)Dh * Dh + (size_t)kNfNodes * Dh) * sizeof(float);
+    static size_t attr[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (smem > 48 * 1024 && smem > attr[dev]) {
+      QAGNN_CHECK_CUDA(cudaFuncSetAttribute(node_feature_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[dev] = smem;
+    }
+    node_feature_fused_kernel<<<(unsigned)((s.N + kNfNodes - 1) / kNfNodes), 256, smem, st>>>(
+        s.N, D, s.T, node_type, node_score, folded + L.type_tab, folded + L.basis, folded + L.ws, folded + L.bs, extra,
+        (__nv_bfloat16*)ex_hi, (__nv_bfloat16*)ex_lo);
+    QAGNN_CHECK_LAUNCH();
+    return QAGNN_OK;
+  }
   const int64_t n = s.N * Dh;
   int64_t g = (n + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
@@ -223,8 +282,10 @@ int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
                                                             folded + L.basis, extra, ws + W.sinb);
   QAGNN_CHECK_LAUNCH();
   // extra[:, D/2:] = GELU(emb_score(sinb))                                  (:73)
-  return sgemm_tn(ws + W.sinb, Dh, Dh, nullptr, 0, 0, folded + L.ws, Dh, folded + L.bs, extra + Dh, D, s.N, Dh,
-                  ACT_GELU, st);
+  QAGNN_RETURN_IF(sgemm_tn(ws + W.sinb, Dh, Dh, nullptr, 0, 0, folded + L.ws, Dh, folded + L.bs, extra + Dh, D, s.N, Dh,
+                           ACT_GELU, st));
+  if (ex_hi != nullptr) QAGNN_RETURN_IF(split_bf16(extra, D, s.N, D, ex_hi, ex_lo, D, st));
+  return QAGNN_OK;
 }
 
 }  // namespace
@@ -328,15 +389,17 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   float* ws = (float*)workspace;
   const float* f = (const float*)folded;
   float* extra = ws + W.extra;
-  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, extra, ws, st));
+  const bool tc = use_tc(s);
+  // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
+  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
+                                tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
   const bool tiled = use_headtile(s);
   if (tiled && !use_tc(s)) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
   const size_t ND = (size_t)s.N * s.D;
-  if (use_tc(s)) {
+  if (tc) {
     const int D = s.D;
     {
       ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
-      QAGNN_RETURN_IF(split_bf16(extra, D, s.N, D, ws + W.ep_hi, ws + W.ep_lo, D, st));
       QAGNN_RETURN_IF(split_bf16(H_in, D, s.N, D, ws + W.hp_hi, ws + W.hp_lo, D, st));
     }
     Planes xin{ws + W.hp_hi, ws + W.hp_lo};
