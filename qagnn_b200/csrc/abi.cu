@@ -107,15 +107,16 @@ __global__ void __launch_bounds__(256) node_feature_fused_kernel(int64_t N, int 
                                                                   const float* __restrict__ ws, const float* __restrict__ bs,
                                                                   float* __restrict__ extra, __nv_bfloat16* __restrict__ ex_hi,
                                                                   __nv_bfloat16* __restrict__ ex_lo) {
-  extern __shared__ float sm_nf[];
-  const int Dh = D / 2;
-  float* Wt = sm_nf;                      // [Dh][Dh]  Wt[k*Dh + j] = ws[j][k]
-  float* Bv = Wt + (size_t)Dh * Dh;       // [kNfNodes][Dh]
+  extern __shared__ __align__(16) float sm_nf[];
+  const int Dh = D / 2;                   // Dh % 4 == 0 (checked by the launcher)
+  float* Wt = sm_nf;                      // [Dh][Dh]        Wt[k*Dh + j] = ws[j][k]
+  float* Bt = Wt + (size_t)Dh * Dh;       // [Dh][kNfNodes]  Bt[k*64 + v] = sin(basis[k] * score[v])
   const int64_t v0 = (int64_t)blockIdx.x * kNfNodes;
   for (int i = threadIdx.x; i < Dh * Dh; i += 256) Wt[(i % Dh) * Dh + i / Dh] = ws[i];
   for (int i = threadIdx.x; i < kNfNodes * Dh; i += 256) {
-    const int64_t v = v0 + i / Dh;
-    Bv[i] = v < N ? sinf(basis[i % Dh] * node_score[v]) : 0.f;  // precise sinf: arguments reach ~1e4 * |score|
+    const int k = i / kNfNodes, vi = i % kNfNodes;
+    const int64_t v = v0 + vi;
+    Bt[i] = v < N ? sinf(basis[k] * node_score[v]) : 0.f;  // precise sinf: arguments reach ~1e4 * |score|
   }
   __syncthreads();
   auto put = [&](int64_t v, int col, float x) {
@@ -126,17 +127,36 @@ __global__ void __launch_bounds__(256) node_feature_fused_kernel(int64_t N, int 
       ex_lo[v * D + col] = __float2bfloat16_rn(x - __bfloat162float(h));
     }
   };
-  for (int o = threadIdx.x; o < kNfNodes * Dh; o += 256) {
-    const int vi = o / Dh, j = o % Dh;
-    const int64_t v = v0 + vi;
-    if (v >= N) continue;
-    float acc = 0.f;
-    const float* b = Bv + vi * Dh;
-    for (int k = 0; k < Dh; ++k) acc = fmaf(b[k], Wt[k * Dh + j], acc);
-    put(v, Dh + j, gelu_tanh(acc + bs[j]));
-    int64_t t = node_type[v];
-    t = t < 0 ? 0 : (t >= T ? T - 1 : t);
-    put(v, j, type_tab[t * Dh + j]);
+  // register tile: 4 nodes x 4 outputs per thread -> two LDS.128 per 16 FMAs
+  const int jg = Dh / 4, ntile = (kNfNodes / 4) * jg;
+  for (int tl = threadIdx.x; tl < ntile; tl += 256) {
+    const int vi0 = (tl / jg) * 4, j0 = (tl % jg) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    for (int k = 0; k < Dh; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(Bt + k * kNfNodes + vi0);
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * Dh + j0);
+      const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(bb[a], ww[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int64_t v = v0 + vi0 + a;
+      if (v >= N) continue;
+      int64_t t = node_type[v];
+      t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        put(v, Dh + j0 + c, gelu_tanh(acc[a][c] + bs[j0 + c]));
+        put(v, j0 + c, type_tab[t * Dh + j0 + c]);
+      }
+    }
   }
 }
 
@@ -261,7 +281,7 @@ int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
                       void* ex_hi = nullptr, void* ex_lo = nullptr) {
   ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   const int D = s.D, Dh = D / 2;
-  if (Dh <= 128) {
+  if (Dh <= 128 && Dh % 4 == 0) {
     const size_t smem = ((size_t)Dh * Dh + (size_t)kNfNodes * Dh) * sizeof(float);
     static size_t attr[kMaxDevices] = {0};
     const int dev = current_device();
@@ -391,7 +411,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   float* extra = ws + W.extra;
   const bool tc = use_tc(s);
   // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
-  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
+  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 && (s.D / 2) % 4 == 0 ? nullptr : extra, ws, st,
                                 tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
   const bool tiled = use_headtile(s);
   if (tiled && !use_tc(s)) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
