@@ -119,12 +119,19 @@ __global__ void __launch_bounds__(256) node_feature_fused_kernel(int64_t N, int 
     Bt[i] = v < N ? sinf(basis[k] * node_score[v]) : 0.f;  // precise sinf: arguments reach ~1e4 * |score|
   }
   __syncthreads();
-  auto put = [&](int64_t v, int col, float x) {
-    if (extra != nullptr) extra[v * D + col] = x;
+  // 4 consecutive columns of one node: one 16-byte fp32 store and/or two 8-byte bf16 stores (hi / lo planes);
+  // (v*D + col) is a multiple of 4 because D % 8 == 0 and col % 4 == 0
+  auto put4 = [&](int64_t v, int col, const float (&x)[4]) {
+    if (extra != nullptr) *reinterpret_cast<float4*>(extra + v * D + col) = make_float4(x[0], x[1], x[2], x[3]);
     if (ex_hi != nullptr) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      ex_hi[v * D + col] = h;
-      ex_lo[v * D + col] = __float2bfloat16_rn(x - __bfloat162float(h));
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        h[c] = __float2bfloat16_rn(x[c]);
+        l[c] = __float2bfloat16_rn(x[c] - __bfloat162float(h[c]));
+      }
+      *reinterpret_cast<uint2*>(ex_hi + v * D + col) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(ex_lo + v * D + col) = *reinterpret_cast<const uint2*>(l);
     }
   };
   // register tile: 4 nodes x 4 outputs per thread -> two LDS.128 per 16 FMAs
@@ -151,11 +158,14 @@ __global__ void __launch_bounds__(256) node_feature_fused_kernel(int64_t N, int 
       if (v >= N) continue;
       int64_t t = node_type[v];
       t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+      float sc[4], ty[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        put(v, Dh + j0 + c, gelu_tanh(acc[a][c] + bs[j0 + c]));
-        put(v, j0 + c, type_tab[t * Dh + j0 + c]);
+        sc[c] = gelu_tanh(acc[a][c] + bs[j0 + c]);
+        ty[c] = type_tab[t * Dh + j0 + c];
       }
+      put4(v, Dh + j0, sc);
+      put4(v, j0, ty);
     }
   }
 }
@@ -281,7 +291,7 @@ int32_t extra_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
                       void* ex_hi = nullptr, void* ex_lo = nullptr) {
   ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   const int D = s.D, Dh = D / 2;
-  if (Dh <= 128 && Dh % 4 == 0) {
+  if (Dh <= 128 && D % 8 == 0) {
     const size_t smem = ((size_t)Dh * Dh + (size_t)kNfNodes * Dh) * sizeof(float);
     static size_t attr[kMaxDevices] = {0};
     const int dev = current_device();
@@ -411,7 +421,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   float* extra = ws + W.extra;
   const bool tc = use_tc(s);
   // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
-  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 && (s.D / 2) % 4 == 0 ? nullptr : extra, ws, st,
+  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
                                 tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
   const bool tiled = use_headtile(s);
   if (tiled && !use_tc(s)) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
