@@ -147,13 +147,54 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int ACT, int BK>
+// ---- 2-CTA (cta_group::2) variants: the CTA pair of a cluster computes a 256-row tile; each CTA stages its own 128 rows of
+// A and HALF of the W tile (the tensor core reads both halves), which cuts the W bytes through the operand ring in two.
+// Patterns follow cute/arch/copy_sm100_tma.hpp (SM100_TMA_2SM_LOAD), cutlass/arch/barrier.h (umma_arrive_multicast_2x1SM).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the even CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar) & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on the same barrier offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the even CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <int ACT, int BK, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 2;              // one A plane tile: 16 KB
-  const uint32_t w_bytes = (uint32_t)p.umma_n * BK * 2;
+  const uint32_t wn = (uint32_t)p.umma_n / CTAS;     // W rows this CTA stages
+  const uint32_t w_bytes = wn * BK * 2;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const unsigned cl_id = blockIdx.x / CTAS, n_cl = gridDim.x / CTAS;  // cluster index / count (tile scheduler)
   unsigned char* ctrl = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);       // [stages]  TMA -> MMA
   uint64_t* empty = full + p.stages;                        // [stages]  MMA -> TMA
@@ -167,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   nkb_seg[1] = p.nseg > 1 ? (p.kseg[1] + BK - 1) / BK : 0;
   const int nkb = nkb_seg[0] + nkb_seg[1];
   const int n_tiles = (p.N + p.n_step - 1) / p.n_step;
-  const long long m_tiles = (p.M + BM - 1) / BM;
+  const long long m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS);
   const long long total_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
@@ -177,17 +218,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], kEpiWarps * CTAS);  // one arrival per epilogue warp (of both CTAs: only the leader's copy is used)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {  // both CTAs of the pair, same warp id, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -196,9 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       long long it = 0;  // k-block counter across tiles
       const int w_off = (int)(blockIdx.x % (unsigned)p.wrep) * p.wrep_rows;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (int)(tile % n_tiles) * p.n_step + w_off;
-        const int m0 = (int)((tile / n_tiles) * BM);
+      for (long long tile = cl_id; tile < total_tiles; tile += n_cl) {
+        const int n0 = (int)(tile % n_tiles) * p.n_step + w_off + (int)(rank * wn);
+        const int m0 = (int)((tile / n_tiles) * BM * CTAS + rank * BM);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = (int)(it % p.stages);
           if (it >= p.stages) mbar_wait(&empty[s], (uint32_t)((it / p.stages) - 1) & 1u);
@@ -206,22 +252,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
           const int k_glob = (seg == 0 ? 0 : p.kseg[0]) + k_in_seg;
           unsigned char* st = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], stage_bytes);
-          tma_load_2d(st, &p.a_hi[seg], k_in_seg, m0, &full[s]);
-          tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, m0, &full[s]);
-          tma_load_2d(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
-          tma_load_2d(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+          if (CTAS == 1) {
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_2d(st, &p.a_hi[seg], k_in_seg, m0, &full[s]);
+            tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, m0, &full[s]);
+            tma_load_2d(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
+            tma_load_2d(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+          } else {  // both CTAs' bytes complete on the LEADER's barrier, which expects the pair's total
+            if (leader) mbar_expect_tx(&full[s], 2 * stage_bytes);
+            tma_load_2d_2sm(st, &p.a_hi[seg], k_in_seg, m0, &full[s]);
+            tma_load_2d_2sm(st + a_bytes, &p.a_lo[seg], k_in_seg, m0, &full[s]);
+            tma_load_2d_2sm(st + 2 * a_bytes, &p.w_hi, k_glob, n0, &full[s]);
+            tma_load_2d_2sm(st + 2 * a_bytes + w_bytes, &p.w_lo, k_glob, n0, &full[s]);
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    if (lane == 0 && leader) {  // cta_group::2: the even CTA issues for the pair
       // cute::UMMA::InstrDescriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
       long long it = 0;
       int ti = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      for (long long tile = cl_id; tile < total_tiles; tile += n_cl, ++ti) {
         const int acc = ti & 1;
         if (ti >= 2) {  // the epilogue must have drained this accumulator
           mbar_wait(&acc_empty[acc], (uint32_t)((ti >> 1) - 1) & 1u);
@@ -241,13 +295,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint64_t da_hi = umma_desc<BK>(sa + k * 32), da_lo = umma_desc<BK>(sa + a_bytes + k * 32);
             const uint64_t dw_hi = umma_desc<BK>(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc<BK>(sa + 2 * a_bytes + w_bytes + k * 32);
             if (p.debug & 4) continue;
-            umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
-            umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
-            umma_bf16(tmem_d, da_lo, dw_hi, idesc, 1u);
+            if (CTAS == 1) {
+              umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
+              umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
+              umma_bf16(tmem_d, da_lo, dw_hi, idesc, 1u);
+            } else {
+              umma_bf16_2sm(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
+              umma_bf16_2sm(tmem_d, da_hi, dw_lo, idesc, 1u);
+              umma_bf16_2sm(tmem_d, da_lo, dw_hi, idesc, 1u);
+            }
           }
-          umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+          if (CTAS == 1) umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+          else umma_commit_2sm(&empty[s]);        // frees the stage in both CTAs
         }
-        umma_commit(&acc_full[acc]);
+        if (CTAS == 1) umma_commit(&acc_full[acc]);
+        else umma_commit_2sm(&acc_full[acc]);
       }
     }
   } else {
@@ -262,11 +324,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int per_head = hm_mode ? (DP + 31) / 32 : 0;                      // 32-column blocks per head slab
     const int nblk = hm_mode ? p.hm.H * per_head : (p.n_step + 31) / 32;    // blocks per tile
     int ti = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (long long tile = cl_id; tile < total_tiles; tile += n_cl, ++ti) {
       const int acc = ti & 1;
       const int n_tile = (int)(tile % n_tiles);
       const int n0 = n_tile * p.n_step;
-      const int row0 = (int)((tile / n_tiles) * BM) + quad * 32;  // first row of this warp
+      const int row0 = (int)((tile / n_tiles) * BM * CTAS + rank * BM) + quad * 32;  // first row of this warp
       mbar_wait(&acc_full[acc], (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
@@ -356,15 +418,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       // accumulator drained: hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+      if (lane == 0) {
+        if (CTAS == 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+        else mbar_arrive_leader(&acc_empty[acc]);
+      }
     }
     tma_store_wait_all();  // global writes of this warp's stores are complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -477,11 +544,15 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.kseg[0] = K1;
   p.kseg[1] = K2;
   p.tmem_cols = 512;
+  static const int CTAS = [] {  // QAGNN_TC_2CTA=1: cta_group::2 tiles (cluster of 2 CTAs, 256 rows, half of W per CTA)
+    const char* e = getenv("QAGNN_TC_2CTA");
+    return (e && atoi(e) == 1) ? 2 : 1;
+  }();
   static const int BK = [] {
     const char* e = getenv("QAGNN_TC_BK");
-    return (e && atoi(e) == 32) ? 32 : 64;
+    return (e && atoi(e) == 32 && CTAS == 1) ? 32 : 64;  // the 2-CTA variant is instantiated for BK = 64 only
   }();
-  const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)p.umma_n * BK * 2;
+  const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)(p.umma_n / CTAS) * BK * 2;
   int stages = (int)((226 * 1024 - 1024 - kEpiWarps * kStageBytesPerWarp) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
@@ -493,7 +564,8 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.wrep = W.replicas > 1 ? W.replicas : 1;
   p.wrep_rows = W.replica_rows;
   const long long w_rows = p.wrep > 1 ? (long long)(p.wrep - 1) * p.wrep_rows + N : N;
-  ok = ok && make_map(&p.w_hi, W.hi, w_rows, K1 + K2, W.ld, p.umma_n, BK) && make_map(&p.w_lo, W.lo, w_rows, K1 + K2, W.ld, p.umma_n, BK);
+  ok = ok && make_map(&p.w_hi, W.hi, w_rows, K1 + K2, W.ld, p.umma_n / CTAS, BK) &&
+       make_map(&p.w_lo, W.lo, w_rows, K1 + K2, W.ld, p.umma_n / CTAS, BK);
   // output maps (TMA stores): fp32 boxes of 32 columns x 32 rows (128-byte swizzle), bf16 boxes 32 x 32 (64-byte swizzle)
   if (out.f32 != nullptr) ok = ok && make_out_map(&p.o_f32, out.f32, 4, N, M, 0, (size_t)out.ldc * 4, 0);
   if (out.hm_buf != nullptr)
@@ -518,22 +590,38 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   const int dev_i = current_device();
   size_t& attr = attr_c[dev_i];
   if (smem_bytes > attr) {
-#define QAGNN_SET_ATTR(A, B) \
-  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
-    QAGNN_SET_ATTR(ACT_NONE, 64); QAGNN_SET_ATTR(ACT_RELU, 64); QAGNN_SET_ATTR(ACT_GELU, 64);
-    QAGNN_SET_ATTR(ACT_NONE, 32); QAGNN_SET_ATTR(ACT_RELU, 32); QAGNN_SET_ATTR(ACT_GELU, 32);
+#define QAGNN_SET_ATTR(A, B, Cn) \
+  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B, Cn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
+    QAGNN_SET_ATTR(ACT_NONE, 64, 1); QAGNN_SET_ATTR(ACT_RELU, 64, 1); QAGNN_SET_ATTR(ACT_GELU, 64, 1);
+    QAGNN_SET_ATTR(ACT_NONE, 32, 1); QAGNN_SET_ATTR(ACT_RELU, 32, 1); QAGNN_SET_ATTR(ACT_GELU, 32, 1);
+    QAGNN_SET_ATTR(ACT_NONE, 64, 2); QAGNN_SET_ATTR(ACT_RELU, 64, 2); QAGNN_SET_ATTR(ACT_GELU, 64, 2);
 #undef QAGNN_SET_ATTR
     attr = smem_bytes;
   }
   static int sms_c[kMaxDevices] = {0};
   if (sms_c[dev_i] == 0) QAGNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms_c[dev_i], cudaDevAttrMultiProcessorCount, dev_i));
   const int sms = sms_c[dev_i];
-  const long long total_tiles = (long long)n_tiles * ((M + BM - 1) / BM);
-  const unsigned grid = (unsigned)(total_tiles < sms ? total_tiles : sms);
-#define QAGNN_LAUNCH(A)                                                                  \
-  do {                                                                                   \
-    if (BK == 64) gemm_tc_kernel<A, 64><<<grid, kThreads, smem_bytes, st>>>(p);           \
-    else gemm_tc_kernel<A, 32><<<grid, kThreads, smem_bytes, st>>>(p);                    \
+  const long long total_tiles = (long long)n_tiles * ((M + (long long)BM * CTAS - 1) / ((long long)BM * CTAS));
+  long long units = total_tiles < sms / CTAS ? total_tiles : sms / CTAS;  // CTAs (or CTA pairs) to launch
+  const unsigned grid = (unsigned)(units * CTAS);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = CTAS;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = CTAS == 2 ? 1 : 0;
+#define QAGNN_LAUNCH(A)                                                                          \
+  do {                                                                                           \
+    if (CTAS == 2) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 2>, p));       \
+    else if (BK == 64) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 1>, p));  \
+    else QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 32, 1>, p));                 \
   } while (0)
   if (act == ACT_NONE) QAGNN_LAUNCH(ACT_NONE);
   else if (act == ACT_RELU) QAGNN_LAUNCH(ACT_RELU);
