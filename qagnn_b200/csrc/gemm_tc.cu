@@ -5,8 +5,9 @@
 //
 // Blackwell-native: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands
 // staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring, one elected
-// thread issuing the MMAs, tcgen05.ld epilogue.  Warp roles per CTA (192 threads):
-//     warps 0-3  epilogue      warp 4  TMA producer      warp 5  TMEM alloc + MMA issuer
+// thread issuing the MMAs, tcgen05.ld epilogue, cp.async.bulk.tensor stores.  By default two CTAs of a cluster pair up
+// (cta_group::2, 256-row tiles, each CTA stages half of W).  Warp roles per CTA (320 threads):
+//     warps 0-7  epilogue      warp 8  TMA producer      warp 9  TMEM alloc + MMA issuer
 //
 // Precision: the reference runs these linears in fp32 and parity is 1e-4, which single-pass bf16
 // (2^-9) or tf32 (2^-11) cannot hold.  Operands are therefore stored as SPLIT-BF16 planes
@@ -544,9 +545,9 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.kseg[0] = K1;
   p.kseg[1] = K2;
   p.tmem_cols = 512;
-  static const int CTAS = [] {  // QAGNN_TC_2CTA=1: cta_group::2 tiles (cluster of 2 CTAs, 256 rows, half of W per CTA)
+  static const int CTAS = [] {  // default: cta_group::2 tiles (cluster of 2 CTAs, 256 rows, half of W per CTA); QAGNN_TC_2CTA=0 -> 1-CTA tiles
     const char* e = getenv("QAGNN_TC_2CTA");
-    return (e && atoi(e) == 1) ? 2 : 1;
+    return (e && atoi(e) == 0) ? 1 : 2;
   }();
   static const int BK = [] {
     const char* e = getenv("QAGNN_TC_BK");
