@@ -54,12 +54,12 @@ def b_alg_per_layer(N, E, D):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm (oracle/qagnn_oracle.py), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_graphs, seed=0):
+def cpu_reference_run(steps, warmup, sample_graphs, seed=0, budget_s=None):
+    """Times the CPU restatement on `sample_graphs` graphs of the workload.  With `budget_s` the sample is shrunk
+    (never below 4 graphs) so that warmup+steps forwards fit the budget; steps and warmup are always honoured."""
     from oracle import qagnn_oracle as O
     ncpu = os.cpu_count() or 1
-    inp = O.synth_graph_batch(sample_graphs, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
     sd = O.random_state_dict(CFG["k"], CFG["D"], CFG["T"], CFG["R"], "prod", seed)
-    E = inp["edge_index"].size(1)
     # torch's intra-op pool degrades badly when oversubscribed on many-core hosts: probe a few pool sizes on a
     # small slice and keep the fastest ("all the host threads it can use")
     probe = O.synth_graph_batch(8, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
@@ -74,6 +74,11 @@ def cpu_reference_run(steps, warmup, sample_graphs, seed=0):
         best = min(best, (time.perf_counter() - t0, nt))
     cores = best[1]
     torch.set_num_threads(cores)
+    if budget_s is not None:
+        per_graph = best[0] / 8 * CFG["k"]          # probe = 8 graphs, 1 layer
+        sample_graphs = int(max(4, min(sample_graphs, budget_s / ((steps + warmup) * per_graph))))
+    inp = O.synth_graph_batch(sample_graphs, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
+    E = inp["edge_index"].size(1)
 
     def step():
         return O.message_passing_forward(sd, inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"],
@@ -95,9 +100,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    r = cpu_reference_run(steps, warm, args.cpu_sample_graphs)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference_run(steps, warm, args.cpu_sample_graphs, budget_s=100.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
