@@ -76,6 +76,12 @@ __device__ __forceinline__ void bulk_g2s_chunked(char* dst, const char* src, uin
   for (uint32_t o = 0; o < bytes; o += kChunk) bulk_g2s(dst + o, src + o, min(kChunk, bytes - o), bar);
 }
 
+// 16-byte shared-memory load from a 32-bit shared address (the V == 1 consumers add pre-scaled row offsets to it)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
@@ -101,7 +107,17 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap)
 }
 inline size_t smem_total(const SmemMap& m) { return (size_t)m.meta + 4 * 4 + 16; }
 
-template <int CPL, int QPW>  // float4 chunks per lane; node-quads per consumer warp and graph (1..4)
+// V selects the consumer code: 0 = the round-1 kernel (measured, validated: the default); 1 = the round-2 candidate
+// (QAGNN_MP_VARIANT=1; same data, same results bit for bit, fewer instructions and stalls — see the V == 1 blocks):
+//   * serpentine quad->warp assignment: with degree-sorted quads, (warp, warp+W) gives warp 0 the two heaviest
+//     quads of each half (critical path 1.32x the mean on the cfg2 batch), (warp, 2W-1-warp) gives 1.13x;
+//   * the degree-order entry of the NEXT-next graph is fetched one iteration early, so the Q-row prefetch no longer
+//     waits on a dependent global load at the top of every graph;
+//   * row offsets are pre-multiplied once per edge by the lane that loads the packed ids (one LEA per row chunk
+//     in the edge loop instead of two IMADs);
+//   * phase 1 reduces the 8 lane-partials of 8 edges with a 7-shuffle transposing tree (lane j ends up with the
+//     logit of edge j, the same summation tree as the butterfly) instead of 3 shuffles per edge.
+template <int CPL, int QPW, int V>  // float4 chunks per lane; node-quads per consumer warp and graph (1..4); variant
 __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 576 : 448, 1) mp_headtile_kernel(const HeadTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NCH = p.DP / 4;
@@ -208,12 +224,37 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
   };
 
+  // V == 1 helpers: quad owned by this warp in pass u (serpentine), the degree-order entry and the Q rows apart
+  auto quad_of = [&](int u) { return (u & 1) ? (u + 1) * p.W - 1 - warp : warp + u * p.W; };
+  auto load_order = [&](int g, int quad) {
+    const int slot_i = quad * 4 + qi;
+    return p.order_src[(int64_t)g * p.n + (slot_i < p.n ? slot_i : 0)];
+  };
+  auto load_q_at = [&](int g, int quad, int vl, float4 (&q)[CPL]) {
+    const int64_t v = (int64_t)g * p.n + vl;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      q[k] = (cvalid[k] && quad < nquads) ? __ldg(reinterpret_cast<const float4*>(Qh + v * p.DP) + chunk[k])
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  const float4* tabc[CPL];  // table base + this lane's chunk: a row is then one scaled add away
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) tabc[k] = tab + chunk[k];
+
   long long t_begin = 0, t_wait_tile = 0, t_wait_tab = 0;
   if (p.trace != nullptr) t_begin = clock64();
   // ---------------------------------- phase 1: attention weights ----------------------------------
   float4 qn[QPW][CPL];  // Q rows of this warp's quads, prefetched one graph ahead
+  int vln[QPW];         // V == 1: degree-order entries of the graph whose Q rows are fetched next
+  if constexpr (V >= 1) {
 #pragma unroll
-  for (int u = 0; u < QPW; ++u) load_q(slot, warp + u * p.W, qn[u]);
+    for (int u = 0; u < QPW; ++u) load_q_at(slot, quad_of(u), load_order(slot, quad_of(u)), qn[u]);
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) vln[u] = Gc > 1 ? load_order(slot + p.S, quad_of(u)) : 0;
+  } else {
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) load_q(slot, warp + u * p.W, qn[u]);
+  }
   {
     const long long c0 = p.trace ? clock64() : 0;
     mbar_wait(tabbar, 0);
@@ -227,9 +268,20 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
     for (int u = 0; u < QPW; ++u)
 #pragma unroll
       for (int k = 0; k < CPL; ++k) qc[u][k] = qn[u][k];
-    if (t + 1 < Gc) {
+    if constexpr (V >= 1) {
+      if (t + 1 < Gc) {
 #pragma unroll
-      for (int u = 0; u < QPW; ++u) load_q(g + p.S, warp + u * p.W, qn[u]);
+        for (int u = 0; u < QPW; ++u) load_q_at(g + p.S, quad_of(u), vln[u], qn[u]);
+        if (t + 2 < Gc) {
+#pragma unroll
+          for (int u = 0; u < QPW; ++u) vln[u] = load_order(g + 2 * p.S, quad_of(u));
+        }
+      }
+    } else {
+      if (t + 1 < Gc) {
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) load_q(g + p.S, warp + u * p.W, qn[u]);
+      }
     }
     {
       const long long c0 = p.trace ? clock64() : 0;
@@ -245,8 +297,10 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
     const bool staged = rp[p.n] - base <= p.ecap;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
-      const int quad = warp + u * p.W;
-      if (quad >= nquads) break;
+      const int quad = (V >= 1) ? quad_of(u) : warp + u * p.W;
+      if (quad >= nquads) {
+        if constexpr (V >= 1) continue; else break;
+      }
       const bool nvalid = quad * 4 + qi < p.n;
       const int vl = nvalid ? od[quad * 4 + qi] : 0;  // 4 nodes of similar out-degree per warp
       const int begr = rp[vl] - base;
@@ -254,41 +308,95 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
       int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
       maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
       float skeep = -INFINITY;  // lane j keeps the logit of edge j (j < 8)
-      for (int i0 = 0; i0 < maxdeg; i0 += 8) {
-        int pkv = 0;
-        if (i0 + l8 < deg) pkv = staged ? ia[begr + i0 + l8] : p.pk_src[base + begr + i0 + l8];
-        const int lim = min(8, maxdeg - i0);
-        for (int j = 0; j < lim; j += 2) {
-          const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
-          const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
-          const float4* k0 = kt + (w0 >> 16) * NCH;
-          const float4* e0 = tab + (w0 & 0xffffu) * NCH;
-          const float4* k1 = kt + (w1 >> 16) * NCH;
-          const float4* e1 = tab + (w1 & 0xffffu) * NCH;
-          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      if constexpr (V >= 1) {
+        uint32_t ktc[CPL];  // shared address of tile base + this lane's chunk: a row is one add away
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            // (quarter-warps past their node's degree read row 0 against a discarded result; predicating these loads
-            //  off saves shared-memory wavefronts but cost 143 -> 177 us in issue slots: measured, reverted)
-            const float4 x0 = k0[chunk[k]], y0 = e0[chunk[k]], x1 = k1[chunk[k]], y1 = e1[chunk[k]];
-            a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[u][k]), a0);
-            a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[u][k]), a0);
-            a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[u][k]), a1);
-            a1 = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), hi2(qc[u][k]), a1);
+        for (int k = 0; k < CPL; ++k) ktc[k] = smem_u32(kt + chunk[k]);
+        const bool b4 = (l8 & 4) != 0, b2 = (l8 & 2) != 0, b1 = (l8 & 1) != 0;
+        for (int i0 = 0; i0 < maxdeg; i0 += 8) {
+          uint32_t pko = 0;  // (tile row offset in bytes << 16) | table row offset in float4 units
+          if (i0 + l8 < deg) {
+            const uint32_t pkv = (uint32_t)(staged ? ia[begr + i0 + l8] : p.pk_src[base + begr + i0 + l8]);
+            pko = (((pkv >> 16) * (uint32_t)(NCH * 16)) << 16) | ((pkv & 0xffffu) * (uint32_t)NCH);
           }
-          float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 4);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-          if (i0 == 0) {
-            skeep = (l8 == j) ? s0 : skeep;
-            skeep = (l8 == j + 1) ? s1 : skeep;
-          } else {  // hub nodes (degree > 8): spill the logits to the L2 scratch
-            if (l8 == 0 && i0 + j < deg) p.score[hE + base + begr + i0 + j] = s0;
-            if (l8 == 1 && i0 + j + 1 < deg) p.score[hE + base + begr + i0 + j + 1] = s1;
+          const int lim = min(8, maxdeg - i0);
+          float v[8];  // this lane's partial dot products of the block's 8 edges
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            if (j < lim) {  // warp-uniform
+              const uint32_t w0 = __shfl_sync(0xffffffffu, pko, qbase + j);
+              const uint32_t w1 = __shfl_sync(0xffffffffu, pko, qbase + j + 1);
+              float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) {
+                const float4 x0 = lds128(ktc[k] + (w0 >> 16)), y0 = tabc[k][w0 & 0xffffu];
+                const float4 x1 = lds128(ktc[k] + (w1 >> 16)), y1 = tabc[k][w1 & 0xffffu];
+                a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[u][k]), a0);
+                a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[u][k]), a0);
+                a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[u][k]), a1);
+                a1 = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), hi2(qc[u][k]), a1);
+              }
+              v[j] = a0.x + a0.y;
+              v[j + 1] = a1.x + a1.y;
+            }
+          }
+          // transposing reduction over the 8 lanes of the node: after the three stages lane j holds
+          // ((v_j[l] + v_j[l^4]) + (v_j[l^2] + v_j[l^6])) + (...[l^1]...), l = j — the butterfly's tree at lane j
+          float r4[4], r2[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+            r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = b2 ? r4[i + 2] : r4[i], send = b2 ? r4[i] : r4[i + 2];
+            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          const float keep = b1 ? r2[1] : r2[0], send = b1 ? r2[0] : r2[1];
+          const float sj = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          if (i0 == 0) skeep = sj;
+          else if (i0 + l8 < deg) p.score[hE + base + begr + i0 + l8] = sj;  // hub nodes: logits past the 8th edge
+        }
+      } else {
+        for (int i0 = 0; i0 < maxdeg; i0 += 8) {
+          int pkv = 0;
+          if (i0 + l8 < deg) pkv = staged ? ia[begr + i0 + l8] : p.pk_src[base + begr + i0 + l8];
+          const int lim = min(8, maxdeg - i0);
+          for (int j = 0; j < lim; j += 2) {
+            const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
+            const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
+            const float4* k0 = kt + (w0 >> 16) * NCH;
+            const float4* e0 = tab + (w0 & 0xffffu) * NCH;
+            const float4* k1 = kt + (w1 >> 16) * NCH;
+            const float4* e1 = tab + (w1 & 0xffffu) * NCH;
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              // (quarter-warps past their node's degree read row 0 against a discarded result; predicating these loads
+              //  off saves shared-memory wavefronts but cost 143 -> 177 us in issue slots: measured, reverted)
+              const float4 x0 = k0[chunk[k]], y0 = e0[chunk[k]], x1 = k1[chunk[k]], y1 = e1[chunk[k]];
+              a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[u][k]), a0);
+              a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[u][k]), a0);
+              a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[u][k]), a1);
+              a1 = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), hi2(qc[u][k]), a1);
+            }
+            float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 4);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            if (i0 == 0) {
+              skeep = (l8 == j) ? s0 : skeep;
+              skeep = (l8 == j + 1) ? s1 : skeep;
+            } else {  // hub nodes (degree > 8): spill the logits to the L2 scratch
+              if (l8 == 0 && i0 + j < deg) p.score[hE + base + begr + i0 + j] = s0;
+              if (l8 == 1 && i0 + j + 1 < deg) p.score[hE + base + begr + i0 + j + 1] = s1;
+            }
           }
         }
       }
@@ -326,8 +434,13 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
         }
       }
     }
-    __threadfence_block();
-    asm volatile("fence.proxy.async;" ::: "memory");  // a'[e] is read back by cp.async.bulk (async proxy) in phase 2
+    // a'[e] is read back by cp.async.bulk (async proxy) in phase 2.  The loader switches phase after the arrivals of
+    // the last two graphs, so one fence before each of those covers all of this thread's earlier stores (V >= 2);
+    // per graph the fence was 5 % of the warp stall samples (profiles/r1_mp_stall_breakdown.md).
+    if (V < 2 || t >= Gc - 2) {
+      __threadfence_block();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[b]);
   }
@@ -355,8 +468,10 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
     const bool staged = rp[p.n] - base <= p.ecap;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
-      const int quad = warp + u * p.W;
-      if (quad >= nquads) break;
+      const int quad = (V >= 1) ? quad_of(u) : warp + u * p.W;
+      if (quad >= nquads) {
+        if constexpr (V >= 1) continue; else break;
+      }
       const bool nvalid = quad * 4 + qi < p.n;
       const int vl = nvalid ? od[quad * 4 + qi] : 0;  // 4 nodes of similar in-degree per warp
       const int begr = rp[vl] - base;
@@ -366,31 +481,66 @@ __global__ void __launch_bounds__(QPW == 1 ? 1024 : QPW == 2 ? 832 : QPW == 3 ? 
       float2 acc[CPL][2];
 #pragma unroll
       for (int k = 0; k < CPL; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
-      for (int i0 = 0; i0 < maxdeg; i0 += 8) {
-        int pkv = 0;
-        float wv = 0.f;
-        if (i0 + l8 < deg) {
-          pkv = staged ? ia[begr + i0 + l8] : p.pk_tgt[base + begr + i0 + l8];
-          wv = staged ? ib[begr + i0 + l8] : p.alpha[hE + base + begr + i0 + l8];
-        }
-        const int lim = min(8, maxdeg - i0);
-        for (int j = 0; j < lim; j += 2) {
-          const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
-          const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
-          const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);      // 0 beyond this node's degree
-          const float a1 = __shfl_sync(0xffffffffu, wv, qbase + j + 1);
-          const float4* m0 = mt + (w0 >> 16) * NCH;
-          const float4* e0 = tab + (w0 & 0xffffu) * NCH;
-          const float4* m1 = mt + (w1 >> 16) * NCH;
-          const float4* e1 = tab + (w1 & 0xffffu) * NCH;
-          const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
+      if constexpr (V >= 1) {
+        uint32_t mtc[CPL];  // shared address of tile base + this lane's chunk
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            const float4 x0 = m0[chunk[k]], y0 = e0[chunk[k]], x1 = m1[chunk[k]], y1 = e1[chunk[k]];
-            acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
-            acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
-            acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
-            acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), aa1, acc[k][1]);
+        for (int k = 0; k < CPL; ++k) mtc[k] = smem_u32(mt + chunk[k]);
+        for (int i0 = 0; i0 < maxdeg; i0 += 8) {
+          uint32_t pko = 0;  // (tile row offset in bytes << 16) | table row offset in float4 units
+          float wv = 0.f;
+          if (i0 + l8 < deg) {
+            const uint32_t pkv = (uint32_t)(staged ? ia[begr + i0 + l8] : p.pk_tgt[base + begr + i0 + l8]);
+            pko = (((pkv >> 16) * (uint32_t)(NCH * 16)) << 16) | ((pkv & 0xffffu) * (uint32_t)NCH);
+            wv = staged ? ib[begr + i0 + l8] : p.alpha[hE + base + begr + i0 + l8];
+          }
+          const int lim = min(8, maxdeg - i0);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            if (j < lim) {  // warp-uniform
+              const uint32_t w0 = __shfl_sync(0xffffffffu, pko, qbase + j);
+              const uint32_t w1 = __shfl_sync(0xffffffffu, pko, qbase + j + 1);
+              const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);      // 0 beyond this node's degree
+              const float a1 = __shfl_sync(0xffffffffu, wv, qbase + j + 1);
+              const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) {
+                const float4 x0 = lds128(mtc[k] + (w0 >> 16)), y0 = tabc[k][w0 & 0xffffu];
+                const float4 x1 = lds128(mtc[k] + (w1 >> 16)), y1 = tabc[k][w1 & 0xffffu];
+                acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
+                acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
+                acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
+                acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), aa1, acc[k][1]);
+              }
+            }
+          }
+        }
+      } else {
+        for (int i0 = 0; i0 < maxdeg; i0 += 8) {
+          int pkv = 0;
+          float wv = 0.f;
+          if (i0 + l8 < deg) {
+            pkv = staged ? ia[begr + i0 + l8] : p.pk_tgt[base + begr + i0 + l8];
+            wv = staged ? ib[begr + i0 + l8] : p.alpha[hE + base + begr + i0 + l8];
+          }
+          const int lim = min(8, maxdeg - i0);
+          for (int j = 0; j < lim; j += 2) {
+            const uint32_t w0 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j);
+            const uint32_t w1 = (uint32_t)__shfl_sync(0xffffffffu, pkv, qbase + j + 1);
+            const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);      // 0 beyond this node's degree
+            const float a1 = __shfl_sync(0xffffffffu, wv, qbase + j + 1);
+            const float4* m0 = mt + (w0 >> 16) * NCH;
+            const float4* e0 = tab + (w0 & 0xffffu) * NCH;
+            const float4* m1 = mt + (w1 >> 16) * NCH;
+            const float4* e1 = tab + (w1 & 0xffffu) * NCH;
+            const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const float4 x0 = m0[chunk[k]], y0 = e0[chunk[k]], x1 = m1[chunk[k]], y1 = e1[chunk[k]];
+              acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
+              acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
+              acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
+              acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), aa1, acc[k][1]);
+            }
           }
         }
       }
@@ -498,16 +648,16 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   return pl;
 }
 
-template <int CPL, int QPW>
+template <int CPL, int QPW, int V>
 int32_t launch_t(const HeadTileParams& p, const HeadTilePlan& plan, unsigned grid, unsigned block, cudaStream_t st) {
   static size_t attr_smem[kMaxDevices] = {0};  // the attribute is per device
   const int dev = current_device();
   if (plan.smem > attr_smem[dev]) {
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL, QPW, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)plan.smem));
     attr_smem[dev] = plan.smem;
   }
-  mp_headtile_kernel<CPL, QPW><<<grid, block, plan.smem, st>>>(p);
+  mp_headtile_kernel<CPL, QPW, V><<<grid, block, plan.smem, st>>>(p);
   QAGNN_CHECK_LAUNCH();
   return QAGNN_OK;
 }
@@ -564,14 +714,38 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
                         h[3], (double)h[0] / h[3], 100.0 * h[1] / h[0], 100.0 * h[2] / h[0]);
     }
   } dump{trace_on, trace_buf, st};
-  if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1>(p, plan, grid, block, st);
-  if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2>(p, plan, grid, block, st);
-  if (plan.cpl == 1 && plan.qpw == 3) return launch_t<1, 3>(p, plan, grid, block, st);
-  if (plan.cpl == 1 && plan.qpw == 4) return launch_t<1, 4>(p, plan, grid, block, st);
-  if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1>(p, plan, grid, block, st);
-  if (plan.cpl == 2 && plan.qpw == 3) return launch_t<2, 3>(p, plan, grid, block, st);
-  if (plan.cpl == 2 && plan.qpw == 4) return launch_t<2, 4>(p, plan, grid, block, st);
-  return launch_t<2, 2>(p, plan, grid, block, st);
+  // QAGNN_MP_VARIANT=1: the round-2 candidate consumer code (see the kernel's header); not the default until it has
+  // been through the GPU parity suite and the bench on a B200
+  const char* variant_env = getenv("QAGNN_MP_VARIANT");  // read per launch: tools/check_mp_variant.py flips it in-process
+  const int variant = variant_env ? atoi(variant_env) : 0;
+  if (variant == 2 && (long)p.n * p.DP * 4 < 65536) {  // = variant 1 + the proxy fence only before the phase switch
+    if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 3) return launch_t<1, 3, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 4) return launch_t<1, 4, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 3) return launch_t<2, 3, 2>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 4) return launch_t<2, 4, 2>(p, plan, grid, block, st);
+    return launch_t<2, 2, 2>(p, plan, grid, block, st);
+  }
+  if (variant == 1 && (long)p.n * p.DP * 4 < 65536) {  // byte offsets of tile rows are packed into 16 bits
+    if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 3) return launch_t<1, 3, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 1 && plan.qpw == 4) return launch_t<1, 4, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 3) return launch_t<2, 3, 1>(p, plan, grid, block, st);
+    if (plan.cpl == 2 && plan.qpw == 4) return launch_t<2, 4, 1>(p, plan, grid, block, st);
+    return launch_t<2, 2, 1>(p, plan, grid, block, st);
+  }
+  if (plan.cpl == 1 && plan.qpw == 1) return launch_t<1, 1, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 2) return launch_t<1, 2, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 3) return launch_t<1, 3, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 1 && plan.qpw == 4) return launch_t<1, 4, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 1) return launch_t<2, 1, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 3) return launch_t<2, 3, 0>(p, plan, grid, block, st);
+  if (plan.cpl == 2 && plan.qpw == 4) return launch_t<2, 4, 0>(p, plan, grid, block, st);
+  return launch_t<2, 2, 0>(p, plan, grid, block, st);
 }
 
 }  // namespace qagnn
