@@ -11,9 +11,10 @@
 //   * phase 1: Ke_h resident, Kx_h tiles streamed through a 2-deep TMA (cp.async.bulk) ring ->
 //     logits, softmax per source node, rescaled weights a'[e] written in BY-TARGET order (L2);
 //   * phase 2: Me_h swapped in, Mx_h tiles streamed the same way -> aggr[:, h*d:(h+1)*d];
-//   * a loader warp runs one graph ahead of the consumers: it issues the TMA copies and stages the
-//     graph's CSR slice (row pointers, packed local ids, phase-2 weights) into shared memory, so the
-//     consumers' inner loops touch no global memory (the v2 kernel lost >50 % to L2 latency there);
+//   * ONE loader thread runs one graph ahead of the consumers: it issues the TMA bulk copies of the node tile and
+//     of the graph's CSR slice (row pointers, degree-sorted node order, packed local ids, by-target positions /
+//     phase-2 weights) into shared memory, so the consumers' inner loops touch no global memory (the v2 kernel
+//     lost >50 % to L2 latency there);
 //   * consumers: 8 lanes per node (quarter-warp), each lane owning float4 chunks l, l+8 of the padded
 //     head row: a quarter-warp LDS.128 covers 128 contiguous bytes = one conflict-free wavefront;
 //     packed FP32x2 math (FADD2/FFMA2, sm_100a); the dot product needs 3 shuffles; two edges per
@@ -107,8 +108,10 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n, int ecap)
 }
 inline size_t smem_total(const SmemMap& m) { return (size_t)m.meta + 4 * 4 + 16; }
 
-// V selects the consumer code: 0 = the round-1 kernel (measured, validated: the default); 1 = the round-2 candidate
-// (QAGNN_MP_VARIANT=1; same data, same results bit for bit, fewer instructions and stalls — see the V == 1 blocks):
+// V selects the consumer code: 0 = the round-1 kernel (full GPU suite, sanitizers: the default); 1 = the round-2
+// candidate (QAGNN_MP_VARIANT=1; bit-identical results on the B200 and 2 % faster, profiles/r1_mp_stall_breakdown.md —
+// the kernel is bound by the LDS/SHFL pipe, not by instruction issue); 2 = 1 + the proxy fence only before the phase
+// switch (compiled, not yet run).  What V >= 1 changes:
 //   * serpentine quad->warp assignment: with degree-sorted quads, (warp, warp+W) gives warp 0 the two heaviest
 //     quads of each half (critical path 1.32x the mean on the cfg2 batch), (warp, 2W-1-warp) gives 1.13x;
 //   * the degree-order entry of the NEXT-next graph is fetched one iteration early, so the Q-row prefetch no longer

@@ -1,9 +1,9 @@
-"""Compares the candidate consumer code of the tiled message-passing kernel (QAGNN_MP_VARIANT=1, see
+"""Compares the candidate consumer code of the tiled message-passing kernel (QAGNN_MP_VARIANT=1 / 2, see
 qagnn_b200/csrc/mp_headtile.cu) with the default one on a B200: results must be BIT-identical (same summation trees),
 and the message-passing stage time is printed for both.  The variant is chosen once per process (the library reads
 the environment on its first launch), so every (variant, QPW) pair runs in a child process.
 
-    python tools/check_mp_variant.py                 # variants 0 and 1 at the default warps/quad split
+    python tools/check_mp_variant.py                 # variants 0, 1, 2 at the default warps/quad split
     python tools/check_mp_variant.py --qpw 2 3 4     # ... and with fewer, fatter warps
 
 Exit code 0 only if every candidate output equals the default bit for bit.
@@ -72,7 +72,7 @@ def main():
     import torch
     tmp = tempfile.mkdtemp()
     runs = {}
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         for qpw in args.qpw:
             tag = f"v{variant}_qpw{qpw}"
             env = dict(os.environ, QAGNN_MP_VARIANT=str(variant))
