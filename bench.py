@@ -96,6 +96,15 @@ def cpu_reference_run(steps, warmup, sample_graphs, seed=0, budget_s=None):
             "ms_per_step": dt * 1e3}
 
 
+def gemm_roofline(N, D, avg_launch_ms, peaks):
+    """Tensor roofline of the projection GEMM [N,2D]x[2D,3D]: three bf16 passes (hi*hi, hi*lo, lo*hi) per launch."""
+    peak = peaks.get("bf16_tflops", 1590.0)
+    flops = 3 * 2 * N * (2 * D) * (3 * D)
+    achieved = flops / (avg_launch_ms * 1e-3) / 1e12 if avg_launch_ms > 0 else 0.0
+    return {"kernel": "gemm_tc_kernel (projection Q|Kx|Mx)", "bound": "tensor", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "avg_launch_ms": avg_launch_ms}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -334,11 +343,7 @@ def run_b200_arm(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_mp_headtile_ncu.md)
                      "traffic": 191374336 if world == 1 else None},  # 173.0 MB read + 18.3 MB written
         # second-largest kernel: the tcgen05 projection GEMM [N,2D]x[2D,3D], three bf16 passes (hi*hi, hi*lo, lo*hi)
-        "roofline_gemm": (lambda ms_: {"kernel": "gemm_tc_kernel (projection Q|Kx|Mx)", "bound": "tensor",
-                                       "achieved": 3 * 2 * N * 2 * D * 3 * D / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0,
-                                       "peak": peaks.get("bf16_tflops", 1590.0), "unit": "TFLOP/s",
-                                       "frac": (3 * 2 * N * 2 * D * 3 * D / (ms_ * 1e-3) / 1e12) / peaks.get("bf16_tflops", 1590.0) if ms_ > 0 else 0.0,
-                                       "avg_launch_ms": ms_})(prof["projection"][0] / max(prof["projection"][1], 1)),
+        "roofline_gemm": gemm_roofline(N, D, prof["projection"][0] / max(prof["projection"][1], 1), peaks),
         "stages": stages,
         "clocks": clocks,
     }
