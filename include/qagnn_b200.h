@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define QAGNN_ABI_VERSION 1
+#define QAGNN_ABI_VERSION 2
 
 enum {
   QAGNN_OK = 0,
@@ -118,6 +118,8 @@ typedef struct qagnn_prep_layout {
   size_t csr_src_tpos; /* [E'] position of edge perm_src[p] in the by-target order       */
   size_t order_src;    /* [N]  per sub-graph: local node ids sorted by out-degree, descending (n_per_graph > 0) */
   size_t order_tgt;    /* [N]  same by in-degree: the tiled kernel gives each warp 4 nodes of similar degree   */
+  size_t ninfo_src;    /* [N] x 2 words, per sub-graph in order_src order: {local id | min(out-degree, 65535) << 16, rowptr_src[v]} */
+  size_t ninfo_tgt;    /* [N] x 2 words, same in order_tgt order with the in-degree and rowptr_tgt[v] (n_per_graph > 0)   */
   size_t status;       /* [4]  device-side error word + counters                        */
   size_t scratch;      /* internal                                                     */
 } qagnn_prep_layout;

@@ -41,7 +41,8 @@ class MPParams(C.Structure):
 class PrepLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total_bytes", "src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src",
                                           "perm_tgt", "csr_src_tgt", "csr_src_combo", "csr_tgt_src", "csr_tgt_combo",
-                                          "csr_tgt_apos", "pk_src", "pk_tgt", "csr_src_tpos", "order_src", "order_tgt", "status", "scratch")]
+                                          "csr_tgt_apos", "pk_src", "pk_tgt", "csr_src_tpos", "order_src", "order_tgt", "ninfo_src", "ninfo_tgt",
+                                          "status", "scratch")]
 
 
 EXPORTS = {
@@ -90,7 +91,7 @@ def load():
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.qagnn_abi_version() != 1:
+    if lib.qagnn_abi_version() != 2:
         raise RuntimeError("libqagnn_b200.so ABI version mismatch")
     _lib = lib
     return lib

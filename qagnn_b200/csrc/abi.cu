@@ -74,6 +74,7 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   const size_t Eps = (Ep + 3) / 4 * 4;  // per-head stride of the tiled path
   W.score = take(Eps * H);
   W.alpha = take(Eps * H);
+  W.alpha2 = take(2 * Eps * H);
   W.total = o;
   return W;
 }
@@ -208,7 +209,7 @@ int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
     if (tiled) {
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
-                                                      ws + W.score, ws + W.alpha, aggr, alpha_out, nullptr, nullptr, st));
+                                                      ws + W.score, ws + W.alpha2, aggr, alpha_out, nullptr, nullptr, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
                                              ws + W.alpha, aggr, alpha_out, st));
@@ -263,7 +264,7 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
     ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
     if (tiled) {
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
-                                                      ws + W.score, ws + W.alpha, aggr, alpha_out,
+                                                      ws + W.score, ws + W.alpha2, aggr, alpha_out,
                                                       fused_split ? ws + W.ap_hi : nullptr, ws + W.ap_lo, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,

@@ -103,7 +103,8 @@ struct WorkLayout {
   size_t ap_hi, ap_lo;          // aggr
   size_t mp_hi, mp_lo;          // mlp hidden
   size_t score;   // [E', H]  raw logits / exp scratch (by-source order)
-  size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order)
+  size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order; general CSR path)
+  size_t alpha2;  // [H, E'] x 2 words  tiled path: {row offsets, a'} per edge and head in by-target order
   size_t total;   // floats
 };
 WorkLayout make_work_layout(const qagnn_shape& s);
@@ -150,7 +151,7 @@ inline int head_dim_padded(int d) { return (d + 3) / 4 * 4; }
 bool headtile_supported(const qagnn_shape& s);
 int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
                                         const float* qkmh, const float* keh, const float* meh, float* score,
-                                        float* alpha, float* aggr, float* alpha_out, void* aggr_hi, void* aggr_lo,
+                                        float* alpha2, float* aggr, float* alpha_out, void* aggr_hi, void* aggr_lo,
                                         cudaStream_t st);
 int32_t zero_head_pads(const qagnn_shape& s, float* qkmh, cudaStream_t st);
 

@@ -239,10 +239,12 @@ __global__ void prep_tpos_kernel(int64_t Ep, const int32_t* __restrict__ perm_sr
 // shared-memory atomic counter: the order only schedules work, it never changes a summation order.
 __global__ void __launch_bounds__(256) prep_degree_order_kernel(int npg, const int32_t* __restrict__ rowptr_src,
                                                                 const int32_t* __restrict__ rowptr_tgt,
-                                                                int32_t* __restrict__ order_src, int32_t* __restrict__ order_tgt) {
+                                                                int32_t* __restrict__ order_src, int32_t* __restrict__ order_tgt,
+                                                                uint2* __restrict__ ninfo_src, uint2* __restrict__ ninfo_tgt) {
   __shared__ int hist[256], base[256];
   const int32_t* rowptr = blockIdx.y ? rowptr_tgt : rowptr_src;
   int32_t* order = (blockIdx.y ? order_tgt : order_src) + (size_t)blockIdx.x * npg;
+  uint2* ninfo = (blockIdx.y ? ninfo_tgt : ninfo_src) + (size_t)blockIdx.x * npg;
   const int64_t v0 = (int64_t)blockIdx.x * npg;
   hist[threadIdx.x] = 0;
   __syncthreads();
@@ -254,8 +256,12 @@ __global__ void __launch_bounds__(256) prep_degree_order_kernel(int npg, const i
   }
   __syncthreads();
   for (int i = threadIdx.x; i < npg; i += 256) {
-    const int b = min(rowptr[v0 + i + 1] - rowptr[v0 + i], 255);
-    order[atomicAdd(&base[b], 1)] = i;
+    const int beg = rowptr[v0 + i], deg = rowptr[v0 + i + 1] - beg;
+    const int b = min(deg, 255);
+    const int slot = atomicAdd(&base[b], 1);
+    order[slot] = i;
+    // what a warp of the tiled kernel needs to start on this node, in one 8-byte load: local id | degree, CSR begin
+    ninfo[slot] = make_uint2((uint32_t)i | ((uint32_t)min(deg, 0xffff) << 16), (uint32_t)beg);
   }
 }
 
@@ -293,6 +299,8 @@ extern "C" int32_t qagnn_graph_prep_layout(int64_t N, int64_t E, qagnn_prep_layo
   out->csr_src_tpos = take(Ep);
   out->order_src = take(N);
   out->order_tgt = take(N);
+  out->ninfo_src = take(2 * (size_t)N);
+  out->ninfo_tgt = take(2 * (size_t)N);
   out->status = take(4);
   out->scratch = o;
   o += make_scratch(N, E).total * 4;
@@ -364,7 +372,8 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
   QAGNN_CHECK_LAUNCH();
   if (npg > 0) {
     prep_degree_order_kernel<<<dim3((unsigned)(N / npg), 2), 256, 0, st>>>(npg, I(pl.rowptr_src), I(pl.rowptr_tgt),
-                                                                          I(pl.order_src), I(pl.order_tgt));
+                                                                          I(pl.order_src), I(pl.order_tgt),
+                                                                          (uint2*)I(pl.ninfo_src), (uint2*)I(pl.ninfo_tgt));
     QAGNN_CHECK_LAUNCH();
   }
   if (validate) {

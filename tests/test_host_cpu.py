@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/qagnn_b200.h but not exported"
     assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
-    assert lib.qagnn_abi_version() == 1
+    assert lib.qagnn_abi_version() == 2
     assert lib.qagnn_status_string(-3).decode().startswith("index out of range")
 
 
