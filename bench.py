@@ -24,6 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CFG = dict(graphs=320, n=200, e=1000, D=200, k=5, H=4, T=4, R=38)
+SENT_DIM = 1024  # RoBERTa-large sentence vector (modeling_encoder.py)
 METRIC = "GNN edges/sec"
 UNIT = "edge-layers/s"
 
@@ -94,6 +95,16 @@ def cpu_reference_run(steps, warmup, sample_graphs, seed=0, budget_s=None):
                       f"forwards of the op-for-op oracle port (torch CPU fp32, {cores} threads = fastest pool size of those probed on "
                       f"this {ncpu}-cpu host), {dt * 1e3:.1f} ms each",
             "ms_per_step": dt * 1e3}
+
+
+def oracle_slice(inp, sd, g0, count):
+    """CPU oracle output for graphs [g0, g0+count) of a workload batch (sub-graphs are independent)."""
+    from oracle import qagnn_oracle as O
+    n = CFG["n"]
+    ei, et = inp["edge_index"], inp["edge_type"]
+    sel = (ei[0] >= g0 * n) & (ei[0] < (g0 + count) * n)
+    return O.message_passing_forward(sd, inp["H"][g0:g0 + count], ei[:, sel] - g0 * n, et[sel], inp["node_type"][g0:g0 + count],
+                                     inp["node_score"][g0:g0 + count], CFG["k"], CFG["T"], CFG["R"], CFG["H"])
 
 
 def gemm_roofline(N, D, avg_launch_ms, peaks):
@@ -168,11 +179,54 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def mp_traffic_from_profile(kernel_sha):
+    """dram bytes (read + write) of one mp_headtile launch from the committed ncu artefact that was captured with the SAME
+    kernel source (profiles/mp_traffic.json: {"mp_headtile_sha16": ..., "dram_bytes": ...}); None when the artefact is
+    missing or belongs to another version of the kernel — never a hard-coded literal."""
+    try:
+        art = json.load(open(os.path.join(ROOT, "profiles", "mp_traffic.json")))
+        return art["dram_bytes"] if art.get("mp_headtile_sha16") == kernel_sha else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def mp_kernel_sha():
+    import hashlib
+    return hashlib.sha256(open(os.path.join(ROOT, "qagnn_b200", "csrc", "mp_headtile.cu"), "rb").read()).hexdigest()[:16]
+
+
+def build_decoder_tail(D, sent_dim, dev):
+    """The pooling layer and answer MLP of the QAGNN decoder around the message passing (modeling_qagnn.py:121-125 with the
+    scripts' defaults: 2 pooling heads, fc_layer_num 0 -> one Linear(2D+sent_dim -> 1); random init, seed 1)."""
+    from qagnn_b200.layers import MLP, MultiheadAttPoolLayer
+    torch.manual_seed(1)
+    pooler = MultiheadAttPoolLayer(2, sent_dim, D).eval().to(dev)
+    fc = MLP(D + sent_dim + D, D, 1, 0, 0.2, layer_norm=True).eval().to(dev)
+    return pooler, fc
+
+
+def synth_step_inputs(rank):
+    """One rank's shard of the workload: the cfg2 graph batch + sentence vectors and graph sizes for the pooling tail."""
+    from oracle import qagnn_oracle as O  # input generator only (shared with the tests)
+    B, n, e, D = CFG["graphs"], CFG["n"], CFG["e"], CFG["D"]
+    inp = O.synth_graph_batch(B, n, e, D, CFG["R"], seed=100 + rank)
+    g = torch.Generator().manual_seed(7000 + rank)
+    inp["sent_vecs"] = torch.randn(B, SENT_DIM, generator=g) * 0.5
+    if "adj_lengths" not in inp or inp["adj_lengths"] is None:
+        inp["adj_lengths"] = torch.full((B,), n, dtype=torch.long)
+    return inp
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
     import torch.distributed as dist
     import qagnn_b200
     from qagnn_b200 import _lib
-    from oracle import qagnn_oracle as O  # input generator only (shared with the tests)
+    from qagnn_b200 import distributed as QD
+    from qagnn_b200.pipeline import DecoderStep, StreamedRunner
+    from oracle import qagnn_oracle as O  # weights generator + the parity gate below; never inside a timed region
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,54 +235,75 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = QD.bind_to_gpu_numa_node(local)  # before any pinned allocation: first touch lands on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
     B, n, e, D, k = CFG["graphs"], CFG["n"], CFG["e"], CFG["D"], CFG["k"]
-    inp = O.synth_graph_batch(B, n, e, D, CFG["R"], seed=100 + rank)
+    inp = synth_step_inputs(rank)
     sd = O.random_state_dict(k, D, CFG["T"], CFG["R"], "prod", seed=0)
     mod = qagnn_b200.QAGNN_Message_Passing(None, k, CFG["T"], CFG["R"], D, D, D).eval()
     mod.load_state_dict(sd)
     mod = mod.to(dev)
+    pooler, fc = build_decoder_tail(D, SENT_DIM, dev)
     N, E = B * n, inp["edge_index"].size(1)
 
-    host = {k_: v.pin_memory() for k_, v in inp.items() if k_ != "adj_lengths"}
+    host = {k_: inp[k_].pin_memory() for k_ in DecoderStep.FIELDS}
     d = {k_: v.to(dev, non_blocking=True) for k_, v in host.items()}
-    out_host = torch.empty(B, n, D, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * B, D, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
 
-    # resident arm: graph prep + all layers replayed as ONE CUDA graph (inputs stay in the same device buffers);
-    # indices are validated once before the capture.  Falls back to per-kernel launches if capture is unavailable.
-    launch_mode = "per-kernel launches"
-    if not args.no_cuda_graph:
-        try:
-            mod.use_cuda_graph = True
-            mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
-            torch.cuda.synchronize()
-            launch_mode = "one CUDA graph per step (prep + 5 layers + epilogue)"
-        except Exception as exc:  # noqa: BLE001
-            mod.use_cuda_graph = False
-            mod._graphs.clear()
-            launch_mode = f"per-kernel launches (CUDA graph capture failed: {type(exc).__name__})"
+    # parity gate: what is about to be timed must match the CPU oracle (first and last 4 graphs of this rank's batch)
+    # within the 1e-4 bar, otherwise the run aborts before any number is produced
+    first = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"]).cpu()
+    parity_err = 0.0
+    for g0 in (0, B - 4):
+        ref = oracle_slice(inp, sd, g0, 4)
+        err = (first[g0:g0 + 4] - ref).abs()
+        if not bool((err <= 1e-4 + 1e-4 * ref.abs()).all()):
+            raise SystemExit(f"bench.py: output of graphs {g0}..{g0 + 3} differs from the oracle (max |err| {err.max().item():.3e})")
+        parity_err = max(parity_err, err.max().item())
+
+    # resident arm: the whole step — graph prep, 5 layers, Vh/Vx, pooling, the all-gather of the pooled features (N > 1)
+    # and the answer MLP — replayed as ONE CUDA graph on static device buffers
+    group = dist.group.WORLD if world > 1 else None
+    try:
+        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=not args.no_cuda_graph)
+    except Exception as exc:  # noqa: BLE001  capture unavailable (e.g. a NCCL build that cannot be captured): per-kernel launches
+        if args.no_cuda_graph:
+            raise
+        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False)
+        step.mode = f"per-kernel launches (CUDA graph capture failed: {type(exc).__name__})"
+    launch_mode = step.mode if step.graph is not None or args.no_cuda_graph else step.mode
+
+    # multi-rank check: every rank must hold the logits a single GPU computes for all N shards (rank 0 recomputes them)
+    logits_err = None
+    if world > 1:
+        got = step.run()[0].clone()
+        torch.cuda.synchronize()
+        if rank == 0:
+            refs = []
+            for r in range(world):
+                ri = synth_step_inputs(r)
+                rd = {k_: ri[k_].to(dev) for k_ in DecoderStep.FIELDS}
+                refs.append(DecoderStep(mod, pooler, fc, rd, 1, None, use_cuda_graph=False).run()[0])
+            ref = torch.cat(refs)
+            logits_err = (got - ref).abs().max().item()
+            if logits_err > 1e-5 + 1e-5 * ref.abs().max().item():
+                raise SystemExit(f"bench.py: {world}-rank logits differ from the single-GPU logits by {logits_err:.3e}")
 
     def step_resident():
-        out = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
-        if world > 1:  # the path's single collective: all-gather of the pooled (context-node) vectors
-            dist.all_gather_into_tensor(gathered, out[:, 0].contiguous())
-        return out
+        step.run()
 
-    # e2e arm: the public streaming API (qagnn_b200.pipeline.StreamedRunner): every step uploads its inputs from pinned
-    # host memory, runs the forward and downloads the [B,n,D] result; copies run on their own streams so that step i+1's
-    # H2D and step i-1's D2H overlap step i's kernels (two device buffer sets, one captured CUDA graph each)
-    from qagnn_b200.pipeline import StreamedRunner
-    runner = StreamedRunner(mod, host, dev, depth=2)
-
-    def step_e2e():
-        slot = runner.submit(host)
-        if world > 1:  # the path's single collective, on the compute stream right after the forward
-            with torch.cuda.stream(runner.compute):
-                dist.all_gather_into_tensor(gathered, runner.dev_out[slot][:, 0].contiguous())
+    # e2e arm: the public streaming API (qagnn_b200.pipeline.StreamedRunner) around the same step: every step uploads its
+    # inputs from pinned host memory and downloads the step's results (logits of the whole job + this rank's pooling
+    # attention); copies run on their own streams, double-buffered (one captured graph per buffer set)
+    def make_step(dev_inputs):
+        return DecoderStep(mod, pooler, fc, dev_inputs, world, group, use_cuda_graph=step.graph is not None)
+    runner = StreamedRunner(mod, host, dev, depth=2, make_step=make_step, fields=DecoderStep.FIELDS, download=(0, 1))
+    # second e2e figure, round 1's definition: bare QAGNN_Message_Passing.forward, [B,n,D] node output downloaded
+    mod.use_cuda_graph = not args.no_cuda_graph
+    runner_nodes = StreamedRunner(mod, host, dev, depth=2)
 
     def barrier():
         if world > 1:
@@ -256,46 +331,43 @@ def run_b200_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches, prof
 
+    def timed_e2e(r, steps):
+        for _ in range(4):
+            r.submit(host)
+        r.drain()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for s_ in (r.h2d, r.compute, r.d2h):
+            s_.wait_event(ev0)
+        for _ in range(steps):
+            r.submit(host)
+        r.drain()
+        ev1.record()
+        barrier()
+        t_ = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return t_.item()
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_total, _, _ = timed(step_resident, args.steps)
-    for _ in range(4):
-        step_e2e()
-    runner.drain()
-
-    def e2e_loop():
-        step_e2e()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for s_ in (runner.h2d, runner.compute, runner.d2h):
-        s_.wait_event(ev0)
-    for _ in range(args.steps):
-        e2e_loop()
-    runner.drain()
-    ev1.record()
-    barrier()
-    t_ = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-    ms_e2e = t_.item()
+    ms_e2e = timed_e2e(runner, args.steps)
+    ms_e2e_nodes = timed_e2e(runner_nodes, args.steps) if world == 1 else None
     # kernel-level pass: the same K steps launched kernel by kernel with the library's CUDA-event stage timers on the
     # launching stream (events cannot be timed inside a replayed graph); feeds `roofline`, `stages`, `gpu_launches`
-    graphed = mod.use_cuda_graph
-    mod.use_cuda_graph = False
-    step_resident()
-    ms_eager, launches, prof = timed(step_resident, args.steps, profile=True)
-    mod.use_cuda_graph = graphed
+    eager = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False)
+    eager.run()
+    ms_eager, launches, prof = timed(eager.run, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
     value = world * k * E / (ms_step * 1e-3)
     e2e_value = world * k * E / (ms_e2e / args.steps * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = out_host.numel() * 4
 
     peaks = {}
     try:
@@ -322,16 +394,19 @@ def run_b200_arm(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(), "graphs_per_gpu": B, "N": N, "E": E, "parallelism": f"dp{world} (sub-graph "
-                   "shards, one NCCL all-gather of pooled vectors)" if world > 1 else "single GPU",
+                   "shards; ONE NCCL all_gather_into_tensor of the pooled features [B, 2D+sent_dim] per step, inside the step's "
+                   "CUDA graph, then the answer MLP on the whole job's batch)" if world > 1 else "single GPU",
                    "l2": f"no flush: a step streams the {lib.qagnn_forward_workspace_bytes(_lib.C.byref(mod._shape(N, E, n))) / 1e6:.0f} MB "
                          "workspace + 51 MB inputs, > 126 MB L2", "step": "graph prep + 5 x (projection, message passing, "
-                   "node MLP) + Vh/Vx epilogue, inputs resident in HBM", "launch": launch_mode},
+                   "node MLP) + Vh/Vx epilogue + attention pooling + (all-gather) + answer MLP, inputs resident in HBM",
+                   "launch": launch_mode, "numa_node_bound": numa},
         "qa_pairs_per_s": world * B / (ms_step * 1e-3),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes(), "d2h_bytes_per_step": runner.d2h_bytes(),
                 "ms_per_step": ms_e2e / args.steps,
-                "api": "qagnn_b200.pipeline.StreamedRunner around QAGNN_Message_Passing.forward: per step H2D of H/edge_index/"
-                       "edge_type/node_type/node_score from pinned host memory, forward, D2H of the [B,n,D] output into pinned "
-                       "memory; copies on separate streams, double-buffered, so they overlap the neighbouring steps' kernels"},
+                "api": "qagnn_b200.pipeline.StreamedRunner around qagnn_b200.pipeline.DecoderStep: per step H2D of H/edge_index/"
+                       "edge_type/node_type/node_score/sent_vecs/adj_lengths from pinned host memory, the step, D2H of its results "
+                       "(logits of the whole job + pooling attention) into pinned memory; copies on separate streams, "
+                       "double-buffered, so they overlap the neighbouring steps' kernels"},
         "gpu_launches": int(launches),
         "gpu_launches_note": "kernels of libqagnn_b200.so enqueued by the K steps of the kernel-level pass (the CUDA graph "
                              "of the headline pass replays the same kernel nodes)",
@@ -340,13 +415,21 @@ def run_b200_arm(args):
                      "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": balg, "avg_launch_ms": mp_avg_ms,
                      "launches_timed": int(mp_cnt),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_mp_headtile_ncu.md)
-                     "traffic": 191374336 if world == 1 else None},  # 173.0 MB read + 18.3 MB written
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu capture of THIS kernel source
+                     "traffic": mp_traffic_from_profile(mp_kernel_sha()) if world == 1 else None},
         # second-largest kernel: the tcgen05 projection GEMM [N,2D]x[2D,3D], three bf16 passes (hi*hi, hi*lo, lo*hi)
         "roofline_gemm": gemm_roofline(N, D, prof["projection"][0] / max(prof["projection"][1], 1), peaks),
         "stages": stages,
+        "parity_gate": {"checked": "graphs 0-3 and %d-%d of the timed batch vs the CPU oracle before timing" % (B - 4, B - 1),
+                        "max_abs_err": parity_err, "bar": "1e-4 + 1e-4*|ref|",
+                        "multi_rank_logits_vs_single_gpu_max_abs_err": logits_err},
         "clocks": clocks,
     }
+    if ms_e2e_nodes is not None:
+        line["e2e_node_output"] = {"value": k * E / (ms_e2e_nodes / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_nodes / args.steps,
+                                   "h2d_bytes_per_step": runner_nodes.h2d_bytes(), "d2h_bytes_per_step": runner_nodes.d2h_bytes(),
+                                   "api": "round 1's definition: StreamedRunner around the bare QAGNN_Message_Passing.forward, the "
+                                          "[B,n,D] node output downloaded every step"}
     if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N=1 only
         r = cpu_reference_run(3, 1, args.cpu_sample_graphs)
         line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}

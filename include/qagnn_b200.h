@@ -14,6 +14,10 @@
  *   qagnn_node_feature_extra  <- QAGNN_Message_Passing.forward prologue   modeling_qagnn.py:62-73,86
  *   qagnn_mp_forward          <- QAGNN_Message_Passing.forward            modeling_qagnn.py:53-95
  *                                (mp_helper :45-50, Vh/Vx epilogue :92)
+ *   qagnn_mp_core_forward /   <- the autograd graph of GATConvE.message + propagate in TRAINING mode
+ *   qagnn_mp_core_backward       (modeling_qagnn.py:442,455-484 under qagnn.py:249-278 loss.backward()):
+ *                                message passing on node-level projections with the attention kept for backward,
+ *                                and its gradient w.r.t. the projections and the two edge tables
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns every
@@ -26,8 +30,9 @@
  *   - return value: 0 = ok, negative = error (qagnn_status_string).  No C++ exceptions cross
  *     the boundary;
  *   - dtypes: features fp32 row-major, indices int64 exactly as the reference's loader
- *     (utils/data_utils.py:79-197) produces them.  Eval-mode forward only (dropout = identity,
- *     BatchNorm running statistics), which is the reference's evaluate_accuracy path (qagnn.py:30-38).
+ *     (utils/data_utils.py:79-197) produces them.  qagnn_gatconve_forward / qagnn_mp_forward are the eval-mode forward
+ *     (dropout = identity, BatchNorm running statistics folded), the reference's evaluate_accuracy path (qagnn.py:30-38);
+ *     training mode composes qagnn_mp_core_forward / _backward with the caller's dense layers (qagnn_b200/training.py).
  */
 #ifndef QAGNN_B200_H_
 #define QAGNN_B200_H_
@@ -170,6 +175,24 @@ int32_t qagnn_node_feature_extra(const qagnn_shape *shape, const int64_t *node_t
 int32_t qagnn_mp_forward(const qagnn_shape *shape, const float *H_in, const int64_t *node_type,
                          const float *node_score, const void *prep, const void *folded, float *out,
                          float *x_layers_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- training --------------------------------------------------------------- */
+
+/* Message passing of one layer on caller-computed node-level projections, keeping what backward needs.
+ *   qkm [N, 3D] row-major = [Q/sqrt(d) | Kx | Mx]  (Q = linear_query([x|extra])/sqrt(d), Kx / Mx = the [x|extra] part of
+ *   linear_key / linear_msg), ke / me [C, D] = edge-table part of linear_key / linear_msg (+ bias) per combo,
+ *   C = R*T*T + T (see qagnn_prep_layout.combo).
+ * Outputs: aggr [N, D] (propagate() output), alpha_scaled [E+N, H] = softmax * out-degree in BY-SOURCE order (saved for
+ * backward), alpha_out (optional) [E+N, H] un-scaled softmax in edge_index' order.  `scratch` = [E+N, H] floats. */
+int32_t qagnn_mp_core_forward(const qagnn_shape *shape, const void *prep, const float *qkm, const float *ke, const float *me,
+                              float *aggr, float *alpha_scaled, float *alpha_out, float *scratch, void *stream);
+
+/* Gradient of qagnn_mp_core_forward: given d_aggr [N, D] writes d_qkm [N, 3D], d_ke / d_me [C, D] (zeroed here first).
+ * combo_order int32 [E+N]: the by-source edge positions stably sorted by qagnn_prep_layout.csr_src_combo (the caller
+ * builds it once per batch).  `scratch` = [E+N, H] floats.  Only dKe / dMe use atomics (a few thousand vector adds). */
+int32_t qagnn_mp_core_backward(const qagnn_shape *shape, const void *prep, const int32_t *combo_order, const float *qkm,
+                               const float *ke, const float *me, const float *alpha_scaled, const float *d_aggr,
+                               float *d_qkm, float *d_ke, float *d_me, float *scratch, void *stream);
 
 /* A stand-alone dense layer on the same tensor-core path the forward uses (diagnostics / tests):
  *   C[M,N] (ldc) = act( [A1 | A2] @ W^T + bias ),  fp32 row-major operands, W [N, K1+K2] (ldw), act 0/1/2 = none/ReLU/GELU(tanh).

@@ -203,6 +203,47 @@ def mint_decoder_case(ref, case, n_ntype=4, n_etype=38):
             "input_fp": fingerprint(inp["H"], inp["edge_index"], sent_vecs, concept_ids)}
 
 
+# training-mode cases: the reference modules in .train() with dropout 0 (the mask stream of a live
+# dropout cannot be reproduced), BatchNorm batch statistics, loss = sum(out * G) for a fixed random G, autograd gradients
+TRAIN_CASES = [
+    dict(name="train_cfg1_peaky_k2", B=4, n=50, e=200, D=64, k=2, regime="peaky", realistic=False, seed=21),
+    dict(name="train_tiny_realistic_d100", B=6, n=24, e=60, D=100, k=3, regime="peaky", realistic=True, seed=22),
+    dict(name="train_cfg2tiny_prod", B=2, n=200, e=1000, D=200, k=2, regime="prod", realistic=False, seed=23),
+]
+
+
+def train_loss_weights(case):
+    g = torch.Generator().manual_seed(9000 + case["seed"])
+    return torch.randn(case["B"], case["n"], case["D"], generator=g)
+
+
+def mint_train_case(ref, case, n_ntype=4, n_etype=38):
+    inp = O.synth_graph_batch(case["B"], case["n"], case["e"], case["D"], n_etype, case["seed"], case["realistic"])
+    sd = O.random_state_dict(case["k"], case["D"], n_ntype, n_etype, case["regime"], case["seed"])
+    mod = ref.QAGNN_Message_Passing(None, k=case["k"], n_ntype=n_ntype, n_etype=n_etype, input_size=case["D"],
+                                    hidden_size=case["D"], output_size=case["D"], dropout=0.0)
+    mod.load_state_dict(sd, strict=True)
+    mod.train()
+    H = inp["H"].clone().requires_grad_(True)
+    score = inp["node_score"].clone().requires_grad_(True)
+    out = mod(H, (inp["edge_index"], inp["edge_type"]), inp["node_type"], score)
+    loss = (out * train_loss_weights(case)).sum()
+    loss.backward()
+    grads = {}
+    seen = set()
+    for name, p_ in mod.named_parameters():  # named_parameters de-duplicates the shared edge_encoder
+        if id(p_) in seen:
+            continue
+        seen.add(id(p_))
+        grads[name] = p_.grad.detach().clone() if p_.grad is not None else None
+    buffers = {name: b.detach().clone() for name, b in mod.named_buffers() if "running" in name or "num_batches" in name}
+    return {"kind": "train", "case": case, "n_ntype": n_ntype, "n_etype": n_etype,
+            "input_fp": fingerprint(inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"], inp["node_score"]),
+            "weight_fp": fingerprint(*[sd[k_] for k_ in sorted(sd) if sd[k_].dtype.is_floating_point]),
+            "out": out.detach().clone(), "loss": float(loss), "grad_H": H.grad.clone(), "grad_score": score.grad.clone(),
+            "grads": grads, "buffers_after": buffers}
+
+
 def main():
     torch.set_num_threads(8)
     ref = load_reference()
@@ -215,6 +256,10 @@ def main():
         fx = mint_layer_case(ref, case)
         torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
         print("minted", case["name"], tuple(fx["out"].shape), float(fx["out"].abs().mean()))
+    for case in TRAIN_CASES:
+        fx = mint_train_case(ref, case)
+        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
+        print("minted", case["name"], fx["loss"], float(fx["grad_H"].abs().mean()))
     for case in DEC_CASES:
         fx = mint_decoder_case(ref, case)
         torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))

@@ -53,10 +53,18 @@ def batchnorm_eval(x, sd, prefix):
     return (x - mean) / torch.sqrt(var + BN_EPS) * sd[prefix + ".weight"].to(dt) + sd[prefix + ".bias"].to(dt)
 
 
-def mlp_lin_bn_relu_lin(x, sd, prefix):
+def batchnorm_train(x, sd, prefix):
+    """torch.nn.BatchNorm1d in training mode: normalises with the biased statistics of the rows of `x`
+    (the running-statistics side effect is not modelled here)."""
+    dt = x.dtype
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    return (x - mean) / torch.sqrt(var + BN_EPS) * sd[prefix + ".weight"].to(dt) + sd[prefix + ".bias"].to(dt)
+
+
+def mlp_lin_bn_relu_lin(x, sd, prefix, train=False):
     """Sequential(Linear, BatchNorm1d, ReLU, Linear) — modeling_qagnn.py:30 and :408."""
     h = linear(x, sd, prefix + ".0")
-    h = torch.relu(batchnorm_eval(h, sd, prefix + ".1"))
+    h = torch.relu(batchnorm_train(h, sd, prefix + ".1") if train else batchnorm_eval(h, sd, prefix + ".1"))
     return linear(h, sd, prefix + ".3")
 
 
@@ -85,13 +93,15 @@ def segment_softmax(src, index):
 # GATConvE  (modeling/modeling_qagnn.py:380-484)
 # ----------------------------------------------------------------------------------------------
 def gatconve_forward(sd, prefix, x, edge_index, edge_type, node_type, node_feature_extra,
-                     n_ntype, n_etype, head_count=4, dtype=torch.float32, edge_encoder_prefix=None):
+                     n_ntype, n_etype, head_count=4, dtype=torch.float32, edge_encoder_prefix=None, train=False):
     """GATConvE.forward + GATConvE.message.
 
     Returns (out [N,D], edge_index' [2,E+N], alpha [E+N,H] (softmax BEFORE the out-degree
     rescale, modeling_qagnn.py:473), aggr [N,D] (propagate output before the node MLP)).
     `prefix` addresses the layer (e.g. 'gnn_layers.0'); the shared edge encoder is read from
     `edge_encoder_prefix` (default f'{prefix}.edge_encoder', an alias of the shared module).
+    train=True: both BatchNorms use batch statistics (the module in .train(), qagnn.py:249); every op is a torch op, so
+    autograd through this function gives the reference's gradients.
     """
     ee = edge_encoder_prefix if edge_encoder_prefix is not None else prefix + ".edge_encoder"
     x = x.to(dtype)
@@ -112,7 +122,7 @@ def gatconve_forward(sd, prefix, x, edge_index, edge_type, node_type, node_featu
     # :431-433
     edge_vec = torch.cat([edge_vec, self_edge_vec], dim=0)
     headtail_vec = torch.cat([headtail_vec, self_headtail_vec], dim=0)
-    edge_emb = mlp_lin_bn_relu_lin(torch.cat([edge_vec, headtail_vec], dim=1), sd, ee)
+    edge_emb = mlp_lin_bn_relu_lin(torch.cat([edge_vec, headtail_vec], dim=1), sd, ee, train)
     # :436-438  self loops appended AFTER the real edges
     loop = torch.arange(N, dtype=torch.long).unsqueeze(0).repeat(2, 1)
     ei = torch.cat([edge_index, loop], dim=1)
@@ -136,7 +146,7 @@ def gatconve_forward(sd, prefix, x, edge_index, edge_type, node_type, node_featu
     # [3P] aggregate: scatter-add by TARGET, dim_size = N
     aggr = scatter_sum(out_msg, tgt, N)
     # :443
-    out = mlp_lin_bn_relu_lin(aggr, sd, prefix + ".mlp")
+    out = mlp_lin_bn_relu_lin(aggr, sd, prefix + ".mlp", train)
     return out, ei, alpha, aggr
 
 

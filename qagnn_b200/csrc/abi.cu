@@ -184,10 +184,8 @@ int32_t check_shape_fwd(const qagnn_shape* s) {
 // (shape.n_per_graph > 0 and the tiles fit), else the general CSR kernels.  QAGNN_MP_PATH=csr forces
 // the general path (A/B measurements).
 bool use_headtile(const qagnn_shape& s) {
-  static const int forced = [] {
-    const char* e = getenv("QAGNN_MP_PATH");
-    return (e && strcmp(e, "csr") == 0) ? 1 : 0;
-  }();
+  const char* e = getenv("QAGNN_MP_PATH");  // read at every call: tests cover both paths in one process
+  const bool forced = e && strcmp(e, "csr") == 0;
   return !forced && headtile_supported(s);
 }
 
@@ -460,6 +458,31 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   // output = GELU(Vh(H) + Vx(X))                                             (:92)
   ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
   return sgemm_tn(H_in, s.D, s.D, x, s.D, s.D, f + L.vcat, 2 * s.D, f + L.vbias, out, s.D, s.N, s.D, ACT_GELU, st);
+}
+
+extern "C" int32_t qagnn_mp_core_forward(const qagnn_shape* shape, const void* prep, const float* qkm, const float* ke,
+                                         const float* me, float* aggr, float* alpha_scaled, float* alpha_out, float* scratch,
+                                         void* stream) {
+  QAGNN_RETURN_IF(check_shape_fwd(shape));
+  if (!prep || !qkm || !ke || !me || !aggr || !alpha_scaled || !scratch) return QAGNN_ERR_INVALID_ARGUMENT;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(shape->N, shape->E, &pl));
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(QAGNN_PROF_MESSAGE_PASSING, st);
+  return launch_message_passing(*shape, (const int32_t*)prep, pl, qkm, ke, me, scratch, alpha_scaled, aggr, alpha_out, st);
+}
+
+extern "C" int32_t qagnn_mp_core_backward(const qagnn_shape* shape, const void* prep, const int32_t* combo_order,
+                                          const float* qkm, const float* ke, const float* me, const float* alpha_scaled,
+                                          const float* d_aggr, float* d_qkm, float* d_ke, float* d_me, float* scratch,
+                                          void* stream) {
+  QAGNN_RETURN_IF(check_shape_fwd(shape));
+  if (!prep || !combo_order || !qkm || !ke || !me || !alpha_scaled || !d_aggr || !d_qkm || !d_ke || !d_me || !scratch)
+    return QAGNN_ERR_INVALID_ARGUMENT;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(shape->N, shape->E, &pl));
+  return launch_message_passing_backward(*shape, (const int32_t*)prep, pl, combo_order, qkm, ke, me, alpha_scaled, d_aggr,
+                                         scratch, d_qkm, d_ke, d_me, (cudaStream_t)stream);
 }
 
 extern "C" size_t qagnn_linear_workspace_bytes(int64_t M, int32_t N, int32_t K1, int32_t K2) {

@@ -131,7 +131,6 @@ struct TcOperand {
   const void* hi;
   const void* lo;
   int ld, K;
-  int replicas = 1, replica_rows = 0;  // weights only: the planes hold `replicas` copies, `replica_rows` rows apart
 };
 // Any subset of: fp32 row-major C, fp32 head-major padded (projection for the tiled MP), split-bf16 planes.
 struct TcOutput {
@@ -158,6 +157,11 @@ int32_t zero_head_pads(const qagnn_shape& s, float* qkmh, cudaStream_t st);
 int32_t launch_message_passing(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
                                const float* qkm, const float* ke, const float* me, float* score, float* alpha,
                                float* aggr, float* alpha_out, cudaStream_t st);
+
+int32_t launch_message_passing_backward(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
+                                        const int32_t* combo_order, const float* qkm, const float* ke, const float* me,
+                                        const float* alpha_s, const float* d_aggr, float* ds, float* d_qkm, float* d_ke,
+                                        float* d_me, cudaStream_t st);
 
 __device__ __forceinline__ float gelu_tanh(float x) {
   // utils/layers.py:10-14

@@ -27,9 +27,7 @@ namespace qagnn {
 namespace {
 
 constexpr int BM = 128;     // rows per CTA tile = UMMA M
-// k-block width in bf16: 64 (128-byte swizzle span, 2 stages of ~85 KB) or 32 (64-byte span, 4 stages of ~43 KB).
-// The ring is latency bound (one stage = TMA round trip + its MMAs), so more, smaller stages move more bytes per
-// second, and the K = 200 tail block wastes half as much (profiles/r1_gemm_tc.md).
+// k-block width in bf16: 64 (one 128-byte swizzle span per row)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 // warps 0-7: epilogue (TMEM lane quadrant = warp id % 4, two warps per quadrant alternate 32-column chunks: with one
@@ -53,8 +51,6 @@ struct alignas(64) TcParams {
   __nv_bfloat16 *c_hi, *c_lo;
   int ldp;
   unsigned tmem_cols;
-  int wrep, wrep_rows;  // W planes replicated wrep times along rows (wrep_rows apart): spreads the hot W lines over L2 slices
-  int debug;  // QAGNN_TC_DEBUG bit mask: 1 skip epilogue stores, 2 skip TMEM loads, 4 skip MMAs (timing experiments)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -242,9 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       long long it = 0;  // k-block counter across tiles
-      const int w_off = (int)(blockIdx.x % (unsigned)p.wrep) * p.wrep_rows;
       for (long long tile = cl_id; tile < total_tiles; tile += n_cl) {
-        const int n0 = (int)(tile % n_tiles) * p.n_step + w_off + (int)(rank * wn);
+        const int n0 = (int)(tile % n_tiles) * p.n_step + (int)(rank * wn);
         const int m0 = (int)((tile / n_tiles) * BM * CTAS + rank * BM);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = (int)(it % p.stages);
@@ -295,7 +290,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int k = 0; k < nsteps; ++k) {
             const uint64_t da_hi = umma_desc<BK>(sa + k * 32), da_lo = umma_desc<BK>(sa + a_bytes + k * 32);
             const uint64_t dw_hi = umma_desc<BK>(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc<BK>(sa + 2 * a_bytes + w_bytes + k * 32);
-            if (p.debug & 4) continue;
             if (CTAS == 1) {
               umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
               umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
@@ -347,13 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if (oc0 >= p.N) break;
         }
         float v[32];
-        if (p.debug & 2) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        } else {
-          tmem_ld32(taddr + (uint32_t)tcol, v);
-        }
-        if (p.debug & 1) continue;
+        tmem_ld32(taddr + (uint32_t)tcol, v);
         if (p.bias != nullptr) {  // bias is indexed by GEMM column (padded like the weight rows)
           if (n0 + tcol + 32 <= p.N) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + tcol);
@@ -500,11 +488,9 @@ bool make_out_map(CUtensorMap* m, void* base, int elem_bytes, long long cols, lo
 
 }  // namespace
 
-bool gemm_tc_available() {
-  static const bool forced_off = [] {
-    const char* e = getenv("QAGNN_GEMM");
-    return e && strcmp(e, "ffma") == 0;
-  }();
+bool gemm_tc_available() {  // QAGNN_GEMM=ffma forces the exact-fp32 FFMA path (read at every call: tests cover both)
+  const char* e = getenv("QAGNN_GEMM");
+  const bool forced_off = e && strcmp(e, "ffma") == 0;
   return !forced_off && encode_fn() != nullptr;
 }
 
@@ -545,14 +531,11 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   p.kseg[0] = K1;
   p.kseg[1] = K2;
   p.tmem_cols = 512;
-  static const int CTAS = [] {  // default: cta_group::2 tiles (cluster of 2 CTAs, 256 rows, half of W per CTA); QAGNN_TC_2CTA=0 -> 1-CTA tiles
-    const char* e = getenv("QAGNN_TC_2CTA");
-    return (e && atoi(e) == 0) ? 1 : 2;
-  }();
-  static const int BK = [] {
-    const char* e = getenv("QAGNN_TC_BK");
-    return (e && atoi(e) == 32 && CTAS == 1) ? 32 : 64;  // the 2-CTA variant is instantiated for BK = 64 only
-  }();
+  // default: cta_group::2 tiles (cluster of 2 CTAs, 256 rows, half of W per CTA); QAGNN_TC_2CTA=0 -> 1-CTA tiles.
+  // Read at every call so that a test can cover both in one process.
+  const char* e2 = getenv("QAGNN_TC_2CTA");
+  const int CTAS = (e2 && atoi(e2) == 0) ? 1 : 2;
+  constexpr int BK = 64;
   const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)(p.umma_n / CTAS) * BK * 2;
   int stages = (int)((226 * 1024 - 1024 - kEpiWarps * kStageBytesPerWarp) / stage_bytes);
   if (stages > 6) stages = 6;
@@ -562,11 +545,8 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   const size_t smem_bytes = stages * stage_bytes + 1024 + kEpiWarps * (size_t)kStageBytesPerWarp;
   bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM, BK) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM, BK);
   if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM, BK) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM, BK);
-  p.wrep = W.replicas > 1 ? W.replicas : 1;
-  p.wrep_rows = W.replica_rows;
-  const long long w_rows = p.wrep > 1 ? (long long)(p.wrep - 1) * p.wrep_rows + N : N;
-  ok = ok && make_map(&p.w_hi, W.hi, w_rows, K1 + K2, W.ld, p.umma_n / CTAS, BK) &&
-       make_map(&p.w_lo, W.lo, w_rows, K1 + K2, W.ld, p.umma_n / CTAS, BK);
+  ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n / CTAS, BK) &&
+       make_map(&p.w_lo, W.lo, N, K1 + K2, W.ld, p.umma_n / CTAS, BK);
   // output maps (TMA stores): fp32 boxes of 32 columns x 32 rows (128-byte swizzle), bf16 boxes 32 x 32 (64-byte swizzle)
   if (out.f32 != nullptr) ok = ok && make_out_map(&p.o_f32, out.f32, 4, N, M, 0, (size_t)out.ldc * 4, 0);
   if (out.hm_buf != nullptr)
@@ -579,7 +559,6 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   if ((out.f32 && (out.ldc % 4 != 0)) || (out.hi && (out.ldp % 8 != 0))) return QAGNN_ERR_UNSUPPORTED;
   p.bias = bias;
   p.act = (int)act;
-  { const char* e = getenv("QAGNN_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.c_f32 = out.f32;
   p.ldc = out.ldc;
   p.c_hm = out.hm_buf;
@@ -594,7 +573,6 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
 #define QAGNN_SET_ATTR(A, B, Cn) \
   QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B, Cn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
     QAGNN_SET_ATTR(ACT_NONE, 64, 1); QAGNN_SET_ATTR(ACT_RELU, 64, 1); QAGNN_SET_ATTR(ACT_GELU, 64, 1);
-    QAGNN_SET_ATTR(ACT_NONE, 32, 1); QAGNN_SET_ATTR(ACT_RELU, 32, 1); QAGNN_SET_ATTR(ACT_GELU, 32, 1);
     QAGNN_SET_ATTR(ACT_NONE, 64, 2); QAGNN_SET_ATTR(ACT_RELU, 64, 2); QAGNN_SET_ATTR(ACT_GELU, 64, 2);
 #undef QAGNN_SET_ATTR
     attr = smem_bytes;
@@ -621,8 +599,7 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
 #define QAGNN_LAUNCH(A)                                                                          \
   do {                                                                                           \
     if (CTAS == 2) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 2>, p));       \
-    else if (BK == 64) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 1>, p));  \
-    else QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 32, 1>, p));                 \
+    else QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 1>, p));                 \
   } while (0)
   if (act == ACT_NONE) QAGNN_LAUNCH(ACT_NONE);
   else if (act == ACT_RELU) QAGNN_LAUNCH(ACT_RELU);

@@ -41,6 +41,7 @@ namespace {
 struct HeadTileParams {
   int64_t N, Eps;  // Eps = per-head stride of score / alpha2 (E' rounded up to 4)
   int n, G, H, D, d, DP, C, S, W, nquads;
+  uint32_t nq_magic;  // floor(2^32 / nquads) + 1: item / nquads == __umulhi(item, nq_magic) for every item a CTA can see
   const int32_t *rowptr_src, *rowptr_tgt, *pk_src, *tpos, *perm_src;
   const uint2 *ninfo_src, *ninfo_tgt;
   const float *qkmh, *keh, *meh;
@@ -110,10 +111,11 @@ __host__ __device__ inline SmemMap make_smem_map(int C, int DP, int n) {
   return m;
 }
 
-constexpr int kMaxConsumerWarps = 24;
+// Consumer warps per CTA: 24 at <= 80 registers, or 31 (a full 1024-thread CTA) at <= 64.
+constexpr int kWarpsWide = 31, kWarpsNarrow = 24;
 
-template <int CPL>  // float4 chunks per lane (1: DP <= 32, 2: DP <= 64)
-__global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_kernel(const HeadTileParams p) {
+template <int CPL, int WMAX>  // CPL: float4 chunks per lane (1: DP <= 32, 2: DP <= 64); WMAX: consumer-warp capacity
+__global__ void __launch_bounds__((WMAX + 1) * 32, 1) mp_headtile_kernel(const HeadTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NCH = p.DP / 4;
   const SmemMap sm = make_smem_map(p.C, p.DP, p.n);
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
     }
     return;
   }
+  if (warp > p.W) return;
 
   // ========================= consumer warps: 4 nodes per warp, 8 lanes per node =========================
   const int l8 = lane & 7, qbase = lane & 24, qi = lane >> 3;
@@ -182,25 +185,32 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
     // and 0 * NaN would poison the shuffled sum (found with compute-sanitizer, whose smem fill is not finite).
     chunk[k] = cvalid[k] ? l8 + 8 * k : l8 % NCH;
   }
-  const float4* tab = reinterpret_cast<const float4*>(smem_raw + sm.tab);
-  const float4* tabc[CPL];  // table base + this lane's chunk: a row is then one scaled add away
+  uint32_t tabu[CPL];  // shared address of the table + this lane's chunk: a row is one add away
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) tabc[k] = tab + chunk[k];
+  for (int k = 0; k < CPL; ++k) tabu[k] = smem_u32(smem_raw + sm.tab) + 16u * (uint32_t)chunk[k];
   const bool b4 = (l8 & 4) != 0, b2 = (l8 & 2) != 0, b1 = (l8 & 1) != 0;
-  const uint32_t row_bytes = (uint32_t)NCH * 16u;
+  const uint32_t nch = (uint32_t)NCH, magic = p.nq_magic;
+  const uint32_t ctr_u32 = smem_u32(ctr);
 
-  auto grab = [&](int* c) {
+  // Offsets word of an edge: low 16 bits = tile-row offset in 16-byte units (< 2^15), high 16 bits = table-row offset in
+  // 2-byte units.  A row address is then base + ((w & 0xffff) << 4) resp. base + (w >> 15)  (bit 15 is always 0).
+  auto offsets_word = [&](uint32_t tile_row, uint32_t table_row) { return (tile_row * nch) | ((table_row * nch * 8u) << 16); };
+  auto tile_addr = [&](uint32_t base, uint32_t w) { return base + ((w & 0xffffu) << 4); };
+  auto table_addr = [&](uint32_t base, uint32_t w) { return base + (w >> 15); };
+
+  auto grab = [&](uint32_t counter) {  // next work item of this phase (one shared-memory atomic per warp)
     int v = 0;
-    if (lane == 0) v = atomicAdd(c, 1);
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(counter) : "memory");
     return __shfl_sync(0xffffffffu, v, 0);
   };
+  auto item_graph = [&](int it) { return (int)__umulhi((uint32_t)it, magic); };  // it / nq
   // packed node record of work item `it` for this lane's node: {local id | degree << 16, CSR begin}; degree 0 = idle
   auto load_ninfo = [&](const uint2* ninfo, int it) {
     uint2 r = make_uint2(0u, 0u);
     if (it < total) {
-      const int t = it / nq, quad = it - t * nq;
-      const int si = quad * 4 + qi;
-      if (si < p.n) r = __ldg(ninfo + (size_t)(slot + t * p.S) * p.n + si);
+      const int t = item_graph(it);
+      const int si = (it - t * nq) * 4 + qi;
+      if (si < p.n) r = __ldg(ninfo + (uint32_t)((slot + t * p.S) * p.n + si));
     }
     return r;
   };
@@ -208,9 +218,9 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
   // ---------------------------------- phase 1: attention weights ----------------------------------
   {
     // software pipeline over work items: it2 = record requested, it1 = Q rows + first 8 edge words requested
-    int it1 = grab(&ctr[0]);
+    int it1 = grab(ctr_u32);
     uint2 ni1 = load_ninfo(p.ninfo_src, it1);
-    int it2 = grab(&ctr[0]);
+    int it2 = grab(ctr_u32);
     uint2 ni2 = load_ninfo(p.ninfo_src, it2);
     float4 q1[CPL];
     int pk1 = 0, tp1 = 0;
@@ -220,11 +230,11 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
 #pragma unroll
       for (int k = 0; k < CPL; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (deg > 0) {  // deg > 0 implies it < total and a valid node
-        const int t = it / nq;
-        const int64_t v = (int64_t)(slot + t * p.S) * p.n + (int)(ni.x & 0xffffu);
+        const uint32_t v = (uint32_t)((slot + item_graph(it) * p.S) * p.n) + (ni.x & 0xffffu);
+        const float4* qrow = reinterpret_cast<const float4*>(Qh) + (size_t)v * nch;
 #pragma unroll
         for (int k = 0; k < CPL; ++k)
-          if (cvalid[k]) q[k] = __ldg(reinterpret_cast<const float4*>(Qh + v * p.DP) + chunk[k]);
+          if (cvalid[k]) q[k] = __ldg(qrow + chunk[k]);
         if (l8 < deg) {
           pk = __ldg(p.pk_src + ni.y + l8);
           tp = __ldg(p.tpos + ni.y + l8);
@@ -243,52 +253,69 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
       int pk0 = pk1, tp0 = tp1;
       it1 = it2; ni1 = ni2;
       issue(it1, ni1, q1, pk1, tp1);
-      it2 = grab(&ctr[0]);
+      it2 = grab(ctr_u32);
       ni2 = load_ninfo(p.ninfo_src, it2);
 
-      const int t = it0 / nq;
+      const int t = item_graph(it0);
       const int b = t & 1;
       if (t != cur_t) {
         mbar_wait(&full[b], (t >> 1) & 1);
         cur_t = t;
       }
-      const int vl = (int)(ni0.x & 0xffffu);
+      const uint32_t vl = ni0.x & 0xffffu;
       const int beg = (int)ni0.y;
       int deg = (int)(ni0.x >> 16);
       if (deg == 0xffff) {  // saturated record: read the true out-degree
         const int64_t v = (int64_t)(slot + t * p.S) * p.n + vl;
         deg = p.rowptr_src[v + 1] - p.rowptr_src[v];
       }
-      int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
-      maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
-      const float4* kt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
+      const int maxdeg = __reduce_max_sync(0xffffffffu, deg);
       uint32_t ktc[CPL];  // shared address of tile base + this lane's chunk: a row is one add away
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) ktc[k] = smem_u32(kt + chunk[k]);
+      for (int k = 0; k < CPL; ++k) ktc[k] = smem_u32(smem_raw + sm.tile0 + b * sm.tile_bytes) + 16u * (uint32_t)chunk[k];
       const size_t sbase = hE + (size_t)beg;
       float skeep = -INFINITY;  // lane j keeps the logit of edge j (j < 8)
       uint32_t pko_first = 0;   // offsets word of edge l8 (first block), kept for the a' record below
       for (int i0 = 0; i0 < maxdeg; i0 += 8) {
         if (i0 > 0) pk0 = (i0 + l8 < deg) ? __ldg(p.pk_src + beg + i0 + l8) : 0;  // hub nodes only
-        uint32_t pko = 0;  // (tile row offset in bytes << 16) | table row offset in float4 units
-        if (i0 + l8 < deg) pko = ((((uint32_t)pk0 >> 16) * row_bytes) << 16) | (((uint32_t)pk0 & 0xffffu) * (uint32_t)NCH);
+        uint32_t pko = 0;
+        if (i0 + l8 < deg) pko = offsets_word((uint32_t)pk0 >> 16, (uint32_t)pk0 & 0xffffu);
         if (i0 == 0) pko_first = pko;
         const int lim = min(8, maxdeg - i0);
+        // the quarter-warp's 8 offsets words, broadcast up front so that no row load waits on a shuffle
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = __shfl_sync(0xffffffffu, pko, qbase + j);
+#pragma unroll
+        for (int j = 4; j < 8; ++j) w[j] = 0u;
+        if (lim > 4) {  // warp-uniform
+#pragma unroll
+          for (int j = 4; j < 8; ++j) w[j] = __shfl_sync(0xffffffffu, pko, qbase + j);
+        }
         float v[8];  // this lane's partial dot products of the block's 8 edges
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        // (quarter-warps past their node's degree read row 0 against a discarded result; predicating these loads
+        //  off saves shared-memory wavefronts but cost 143 -> 177 us in issue slots in round 1: measured, reverted)
+        auto edge1 = [&](uint32_t w0) {
+          float2 a0 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            const float4 x0 = lds128(tile_addr(ktc[k], w0)), y0 = lds128(table_addr(tabu[k], w0));
+            a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[k]), a0);
+            a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[k]), a0);
+          }
+          return a0.x + a0.y;
+        };
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          if (j < lim) {  // warp-uniform
-            const uint32_t w0 = __shfl_sync(0xffffffffu, pko, qbase + j);
-            const uint32_t w1 = __shfl_sync(0xffffffffu, pko, qbase + j + 1);
+          if (j + 1 < lim) {  // warp-uniform
+            const uint32_t w0 = w[j], w1 = w[j + 1];
             float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-              // (quarter-warps past their node's degree read row 0 against a discarded result; predicating these loads
-              //  off saves shared-memory wavefronts but cost 143 -> 177 us in issue slots in round 1: measured, reverted)
-              const float4 x0 = lds128(ktc[k] + (w0 >> 16)), y0 = tabc[k][w0 & 0xffffu];
-              const float4 x1 = lds128(ktc[k] + (w1 >> 16)), y1 = tabc[k][w1 & 0xffffu];
+              const float4 x0 = lds128(tile_addr(ktc[k], w0)), y0 = lds128(table_addr(tabu[k], w0));
+              const float4 x1 = lds128(tile_addr(ktc[k], w1)), y1 = lds128(table_addr(tabu[k], w1));
               a0 = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), lo2(qc[k]), a0);
               a0 = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), hi2(qc[k]), a0);
               a1 = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), lo2(qc[k]), a1);
@@ -296,6 +323,8 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
             }
             v[j] = a0.x + a0.y;
             v[j + 1] = a1.x + a1.y;
+          } else if (j < lim) {  // odd tail: one edge
+            v[j] = edge1(w[j]);
           }
         }
         // transposing reduction over the 8 lanes of the node: after the three stages lane j holds
@@ -335,17 +364,17 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
       // a = ex / (sum + 1e-16) (torch_geometric.utils.softmax), then * out-degree of the source (:476-481)
       const float rden = __fdividef(1.f, ssum + 1e-16f);
       const float degf = (float)deg;
-      const uint32_t src_off = ((uint32_t)vl * row_bytes) << 16;  // row of this SOURCE node in the Mx tile (phase 2)
+      const uint32_t src_off = vl * nch;  // row of this SOURCE node in the Mx tile (phase 2), 16-byte units
       if (l8 < deg) {
         const float a = ex0 * rden;
-        p.alpha2[hE + (size_t)tp0] = make_uint2(src_off | (pko_first & 0xffffu), __float_as_uint(a * degf));
+        p.alpha2[hE + (size_t)tp0] = make_uint2(src_off | (pko_first & 0xffff0000u), __float_as_uint(a * degf));
         if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[beg + l8] * p.H + h] = a;
       }
       if (hub) {
         for (int j = 8 + l8; j < deg; j += 8) {
           const float a = __expf(__ldcg(p.score + sbase + j) - m) * rden;
           const uint32_t combo = (uint32_t)__ldg(p.pk_src + beg + j) & 0xffffu;
-          p.alpha2[hE + (size_t)__ldg(p.tpos + beg + j)] = make_uint2(src_off | (combo * (uint32_t)NCH), __float_as_uint(a * degf));
+          p.alpha2[hE + (size_t)__ldg(p.tpos + beg + j)] = make_uint2(offsets_word(vl, combo), __float_as_uint(a * degf));
           if (p.alpha_out != nullptr) p.alpha_out[(size_t)p.perm_src[beg + j] * p.H + h] = a;
         }
       }
@@ -361,9 +390,9 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
 
   // ---------------------------------- phase 2: weighted sum by target ----------------------------------
   {
-    int it1 = grab(&ctr[1]);
+    int it1 = grab(ctr_u32 + 4);
     uint2 ni1 = load_ninfo(p.ninfo_tgt, it1);
-    int it2 = grab(&ctr[1]);
+    int it2 = grab(ctr_u32 + 4);
     uint2 ni2 = load_ninfo(p.ninfo_tgt, it2);
     uint2 e1 = make_uint2(0u, 0u);  // {offsets word, a'} of this lane's edge among the node's first 8 in-edges
     auto issue = [&](const uint2& ni, uint2& e) {
@@ -380,11 +409,11 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
       uint2 e0 = e1;
       it1 = it2; ni1 = ni2;
       issue(ni1, e1);
-      it2 = grab(&ctr[1]);
+      it2 = grab(ctr_u32 + 4);
       ni2 = load_ninfo(p.ninfo_tgt, it2);
 
-      const int tg = it0 / nq;  // graph index within this CTA's list
-      const int t = Gc + tg;    // ring position
+      const int tg = item_graph(it0);  // graph index within this CTA's list
+      const int t = Gc + tg;           // ring position
       const int b = t & 1;
       if (t != cur_t) {
         mbar_wait(&full[b], (t >> 1) & 1);
@@ -392,17 +421,15 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
       }
       const int quad = it0 - tg * nq;
       const bool nvalid = quad * 4 + qi < p.n;
-      const int vl = (int)(ni0.x & 0xffffu);
+      const uint32_t vl = ni0.x & 0xffffu;
       const int beg = (int)ni0.y;
       const int64_t v = (int64_t)(slot + tg * p.S) * p.n + vl;
       int deg = (int)(ni0.x >> 16);
       if (deg == 0xffff) deg = p.rowptr_tgt[v + 1] - p.rowptr_tgt[v];  // saturated record: read the true in-degree
-      int maxdeg = max(deg, __shfl_xor_sync(0xffffffffu, deg, 8));
-      maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
-      const float4* mt = reinterpret_cast<const float4*>(smem_raw + sm.tile0 + b * sm.tile_bytes);
+      const int maxdeg = __reduce_max_sync(0xffffffffu, deg);
       uint32_t mtc[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) mtc[k] = smem_u32(mt + chunk[k]);
+      for (int k = 0; k < CPL; ++k) mtc[k] = smem_u32(smem_raw + sm.tile0 + b * sm.tile_bytes) + 16u * (uint32_t)chunk[k];
       float2 acc[CPL][2];
 #pragma unroll
       for (int k = 0; k < CPL; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
         const int lim = min(8, maxdeg - i0);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-          if (j < lim) {  // warp-uniform
+          if (j + 1 < lim) {  // warp-uniform
             const uint32_t w0 = __shfl_sync(0xffffffffu, pko, qbase + j);
             const uint32_t w1 = __shfl_sync(0xffffffffu, pko, qbase + j + 1);
             const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);
@@ -424,12 +451,22 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) mp_headtile_k
             const float2 aa0 = make_float2(a0, a0), aa1 = make_float2(a1, a1);
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-              const float4 x0 = lds128(mtc[k] + (w0 >> 16)), y0 = tabc[k][w0 & 0xffffu];
-              const float4 x1 = lds128(mtc[k] + (w1 >> 16)), y1 = tabc[k][w1 & 0xffffu];
+              const float4 x0 = lds128(tile_addr(mtc[k], w0)), y0 = lds128(table_addr(tabu[k], w0));
+              const float4 x1 = lds128(tile_addr(mtc[k], w1)), y1 = lds128(table_addr(tabu[k], w1));
               acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
               acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
               acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x1), lo2(y1)), aa1, acc[k][0]);
               acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x1), hi2(y1)), aa1, acc[k][1]);
+            }
+          } else if (j < lim) {  // odd tail: one edge
+            const uint32_t w0 = __shfl_sync(0xffffffffu, pko, qbase + j);
+            const float a0 = __shfl_sync(0xffffffffu, wv, qbase + j);
+            const float2 aa0 = make_float2(a0, a0);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const float4 x0 = lds128(tile_addr(mtc[k], w0)), y0 = lds128(table_addr(tabu[k], w0));
+              acc[k][0] = __ffma2_rn(__fadd2_rn(lo2(x0), lo2(y0)), aa0, acc[k][0]);
+              acc[k][1] = __ffma2_rn(__fadd2_rn(hi2(x0), hi2(y0)), aa0, acc[k][1]);
             }
           }
         }
@@ -487,8 +524,16 @@ __global__ void zero_head_pads_kernel(int64_t rows, int d, int DP, float* __rest
 struct HeadTilePlan {
   bool ok;
   int DP, C, S, W, cpl, nquads;
+  uint32_t nq_magic;
   size_t smem;
 };
+
+// A/B switch, read at every launch: QAGNN_MP_WARPS=<n> forces the number of consumer warps per CTA (1..31).
+int forced_warps() {
+  const char* e = getenv("QAGNN_MP_WARPS");
+  const int w = e ? atoi(e) : 0;
+  return (w >= 1 && w <= kWarpsWide) ? w : 0;
+}
 
 HeadTilePlan make_plan(const qagnn_shape& s) {
   HeadTilePlan pl{};
@@ -498,8 +543,9 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   pl.DP = head_dim_padded(d);
   pl.C = s.R * s.T * s.T + s.T;
   if (pl.DP > 64) return pl;
-  // the 16|16-bit offset words: byte offset of a tile row, float4 offset of a table row
-  if ((long)(s.n_per_graph - 1) * pl.DP * 4 > 65535 || (long)(pl.C - 1) * (pl.DP / 4) > 65535) return pl;
+  // the 16|16-bit offsets words: tile rows in 16-byte units below 2^15, table rows in 2-byte units below 2^16
+  const long nch = pl.DP / 4;
+  if ((long)(s.n_per_graph - 1) * nch > 32767 || (long)(pl.C - 1) * nch * 8 > 65535) return pl;
   if (s.E + s.N >= ((int64_t)1 << 31)) return pl;
   pl.cpl = pl.DP <= 32 ? 1 : 2;
   static int sms_c[kMaxDevices] = {0}, smem_c[kMaxDevices] = {0};
@@ -514,25 +560,29 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   if ((long)pl.smem > (long)max_smem) return pl;
   pl.S = sms / s.H;
   pl.nquads = (s.n_per_graph + 3) / 4;
+  // item / nquads by multiply-high: exact while item * nquads < 2^32 (items run to graphs-per-CTA * nquads + 2 per warp)
+  pl.nq_magic = (uint32_t)((((uint64_t)1) << 32) / (uint64_t)pl.nquads) + 1u;
+  const long long G = s.N / s.n_per_graph, Gc = (G + pl.S - 1) / pl.S;
+  if ((Gc * pl.nquads + 4 * kWarpsWide) * (long long)pl.nquads >= ((long long)1 << 32)) return pl;
   // two graphs' quads can be in flight at once; more warps than that would only spin
   int W = 2 * pl.nquads;
-  if (W > kMaxConsumerWarps) W = kMaxConsumerWarps;
-  static const int forced_w = [] { const char* e = getenv("QAGNN_MP_WARPS"); return e ? atoi(e) : 0; }();
-  if (forced_w >= 1 && forced_w <= kMaxConsumerWarps) W = forced_w;
+  if (W > kWarpsWide) W = kWarpsWide;
+  const int fw = forced_warps();
+  if (fw) W = fw;
   pl.W = W;
   pl.ok = true;
   return pl;
 }
 
-template <int CPL>
+template <int CPL, int WMAX>
 int32_t launch_t(const HeadTileParams& p, const HeadTilePlan& plan, unsigned grid, unsigned block, cudaStream_t st) {
   static size_t attr_smem[kMaxDevices] = {0};  // the attribute is per device
   const int dev = current_device();
   if (plan.smem > attr_smem[dev]) {
-    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(mp_headtile_kernel<CPL, WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     attr_smem[dev] = plan.smem;
   }
-  mp_headtile_kernel<CPL><<<grid, block, plan.smem, st>>>(p);
+  mp_headtile_kernel<CPL, WMAX><<<grid, block, plan.smem, st>>>(p);
   QAGNN_CHECK_LAUNCH();
   return QAGNN_OK;
 }
@@ -562,15 +612,16 @@ int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* pre
   HeadTileParams p;
   p.N = s.N; p.Eps = (s.N + s.E + 3) / 4 * 4;
   p.n = s.n_per_graph; p.G = (int)(s.N / s.n_per_graph); p.H = s.H; p.D = s.D; p.d = s.D / s.H; p.DP = plan.DP;
-  p.C = plan.C; p.S = plan.S; p.W = plan.W; p.nquads = plan.nquads;
+  p.C = plan.C; p.S = plan.S; p.W = plan.W; p.nquads = plan.nquads; p.nq_magic = plan.nq_magic;
   p.rowptr_src = I(L.rowptr_src); p.rowptr_tgt = I(L.rowptr_tgt); p.pk_src = I(L.pk_src); p.tpos = I(L.csr_src_tpos); p.perm_src = I(L.perm_src);
   p.ninfo_src = (const uint2*)I(L.ninfo_src); p.ninfo_tgt = (const uint2*)I(L.ninfo_tgt);
   p.qkmh = qkmh; p.keh = keh; p.meh = meh; p.score = score; p.alpha2 = (uint2*)alpha2; p.aggr = aggr; p.alpha_out = alpha_out;
   p.aggr_hi = (s.D % 2 == 0 && (s.D / s.H) % 2 == 0) ? aggr_hi : nullptr; p.aggr_lo = aggr_lo;
   if (aggr_hi != nullptr && p.aggr_hi == nullptr) return QAGNN_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)(plan.S * s.H), block = (unsigned)(plan.W + 1) * 32;
-  if (plan.cpl == 1) return launch_t<1>(p, plan, grid, block, st);
-  return launch_t<2>(p, plan, grid, block, st);
+  const bool wide = plan.W > kWarpsNarrow;  // more than 24 consumer warps: the 64-register build
+  if (plan.cpl == 1) return wide ? launch_t<1, kWarpsWide>(p, plan, grid, block, st) : launch_t<1, kWarpsNarrow>(p, plan, grid, block, st);
+  return wide ? launch_t<2, kWarpsWide>(p, plan, grid, block, st) : launch_t<2, kWarpsNarrow>(p, plan, grid, block, st);
 }
 
 }  // namespace qagnn

@@ -24,10 +24,20 @@ def shard_batch(inputs, rank, world_size):
     return tuple(t[lo:hi] for t in tensors) + (edge_index[lo:hi], edge_type[lo:hi]), (lo, hi)
 
 
-def all_gather_rows(local, world_size, group=None):
-    """All-gather of row blocks that may differ in length by rank (the last shard can be short)."""
+def all_gather_rows(local, world_size, group=None, equal_shards=True, out=None):
+    """The path's ONE collective: all-gather of the ranks' row blocks [B_r, F] -> [sum B_r, F].
+
+    equal_shards=True (how `shard_bounds` cuts a batch whose question count divides by the world size, and cfg4 of
+    BASELINE.json): a single `all_gather_into_tensor`, no size exchange, no host synchronisation — capturable in a CUDA
+    graph.  `out` optionally names the [world_size * B_r, F] result buffer (static address for graph replay).
+    equal_shards=False: blocks may differ in length (a short last shard): sizes are exchanged first, then padded blocks."""
     if world_size == 1:
         return local
+    if equal_shards:
+        if out is None:
+            out = local.new_empty((world_size * local.size(0),) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     n = torch.tensor([local.size(0)], device=local.device, dtype=torch.long)
     sizes = [torch.zeros_like(n) for _ in range(world_size)]
     dist.all_gather(sizes, n, group=group)
@@ -41,9 +51,33 @@ def all_gather_rows(local, world_size, group=None):
 
 
 def decoder_forward_sharded(decoder, sent_vecs, concept_ids, node_type_ids, node_scores, adj_lengths, adj, world_size,
-                            group=None):
-    """QAGNN.forward on this rank's shard + all-gather of the pooled features + the answer MLP on the full batch.
-    Returns (logits of ALL graphs [B_total, 1], local pool_attn)."""
+                            group=None, equal_shards=True):
+    """QAGNN.forward on this rank's shard + all-gather of the pooled features + the answer MLP on the full batch
+    (modeling_qagnn.py:172-188).  Returns (logits of ALL graphs [B_total, 1], local pool_attn)."""
     concat, pool_attn = decoder.pooled_features(sent_vecs, concept_ids, node_type_ids, node_scores, adj_lengths, adj)
-    full = all_gather_rows(concat, world_size, group)
+    full = all_gather_rows(concat, world_size, group, equal_shards)
     return decoder.fc(full), pool_attn
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pins this process (and the pinned host buffers it allocates afterwards, by first touch) to the CPUs of the NUMA node
+    the GPU hangs off.  8 ranks streaming ~110 MB per step through pinned memory otherwise cross the socket interconnect
+    for half of the GPUs (SCALE_r01: e2e efficiency 0.74 at N=8 with device-side efficiency 0.97).  Returns the node or None."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 - affinity is an optimisation, never a failure
+        return None

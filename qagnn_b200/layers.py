@@ -74,12 +74,14 @@ class MultiheadAttPoolLayer(nn.Module):
         self.temperature = math.sqrt(self.d_k)
         self.attn_dropout = nn.Dropout(0.1)  # MatrixVectorScaledDotProductAttention's own dropout
         self.dropout = nn.Dropout(dropout)
+        self._fused_ok = True
 
     def forward(self, q, k, mask=None):
         b, l, _ = k.shape
         nh, dk, dv = self.n_head, self.d_k, self.d_v
-        if (k.is_cuda and not self.training and mask is not None and k.dtype == torch.float32
-                and self.w_ks.weight.shape[0] == k.shape[2]):
+        wants_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad)  # the fused kernel is outside autograd
+        if (k.is_cuda and not self.training and not wants_grad and mask is not None and k.dtype == torch.float32
+                and self.w_ks.weight.shape[0] == k.shape[2] and self._fused_ok):
             # fused kernel (one read of k, no ks/vs GEMMs): qagnn_attention_pool
             from . import _lib
             lib = _lib.load()
@@ -93,8 +95,11 @@ class MultiheadAttPoolLayer(nn.Module):
                                               _lib.ptr(self.w_ks.weight.detach()), _lib.ptr(self.w_ks.bias.detach()),
                                               _lib.ptr(self.w_vs.weight.detach()), _lib.ptr(self.w_vs.bias.detach()),
                                               _lib.ptr(pooled), _lib.ptr(attn), _lib.stream_ptr(k.device))
-            _lib.check(st, "qagnn_attention_pool")
-            return pooled, attn
+            if st == -5:  # QAGNN_ERR_UNSUPPORTED (node tile does not fit in shared memory): the einsum path below
+                self._fused_ok = False
+            else:
+                _lib.check(st, "qagnn_attention_pool")
+                return pooled, attn
         qs = self.w_qs(q).view(b, nh, dk)
         ks = self.w_ks(k).view(b, l, nh, dk)
         vs = self.w_vs(k).view(b, l, nh, dv)

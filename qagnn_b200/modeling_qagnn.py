@@ -33,14 +33,31 @@ def _version_key(tensors):
     return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
 
 
-class _DeviceBlob:
-    """A grow-only uint8 device buffer (workspace the C ABI asks the caller to own)."""
+_warned_grad = set()
 
-    def __init__(self):
+
+def _warn_if_grad_wanted(what, *tensors):
+    """The eval-mode forward runs outside autograd (its outputs carry no grad_fn).  Say so once if a caller seems to
+    expect gradients; `.train()` selects the differentiable path (qagnn_b200/training.py)."""
+    if torch.is_grad_enabled() and what not in _warned_grad and any(t is not None and t.requires_grad for t in tensors):
+        import warnings
+        _warned_grad.add(what)
+        warnings.warn(f"qagnn_b200.{what}: eval-mode forward is not differentiable (inputs require grad but the output "
+                      f"has no grad_fn); call .train() for the autograd path")
+
+
+class _DeviceBlob:
+    """A grow-only uint8 device buffer (workspace the C ABI asks the caller to own).  `on_replace` runs before the
+    buffer is dropped for a larger one: captured CUDA graphs hold its raw address and must be discarded first."""
+
+    def __init__(self, on_replace=None):
         self.buf = None
+        self.on_replace = on_replace
 
     def get(self, nbytes, device):
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            if self.buf is not None and self.on_replace is not None:
+                self.on_replace()
             self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         return self.buf
 
@@ -48,7 +65,8 @@ class _DeviceBlob:
 class GraphPrep:
     """Owns the opaque graph-prep workspace of one batched graph (qagnn_graph_prep)."""
 
-    def __init__(self, edge_index, edge_type, node_type, n_ntype, n_etype, n_per_graph=0, validate=True):
+    def __init__(self, edge_index, edge_type, node_type, n_ntype, n_etype, n_per_graph=0, validate=True,
+                 allow_general_fallback=False):
         lib = _lib.load()
         ei = _lib.i64c(edge_index, "edge_index")
         et = _lib.i64c(edge_type, "edge_type")
@@ -61,13 +79,36 @@ class GraphPrep:
         self.layout = _lib.PrepLayout()
         _lib.check(lib.qagnn_graph_prep_layout(self.N, self.E, C.byref(self.layout)), "qagnn_graph_prep_layout")
         self.buf = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
-        shape = _lib.Shape(self.N, self.E, 4, 1, n_ntype, n_etype, 0, self.n_per_graph)
-        with torch.cuda.device(self.device):
-            st = lib.qagnn_graph_prep(_lib.ptr(ei) if self.E else None, _lib.ptr(et) if self.E else None, _lib.ptr(nt),
-                                      C.byref(shape), _lib.ptr(self.buf), self.buf.numel(), int(bool(validate)),
-                                      _lib.stream_ptr(self.device))
+        self._combo_order = None
+
+        def run():
+            shape = _lib.Shape(self.N, self.E, 4, 1, n_ntype, n_etype, 0, self.n_per_graph)
+            with torch.cuda.device(self.device):
+                return lib.qagnn_graph_prep(_lib.ptr(ei) if self.E else None, _lib.ptr(et) if self.E else None, _lib.ptr(nt),
+                                            C.byref(shape), _lib.ptr(self.buf), self.buf.numel(), int(bool(validate)),
+                                            _lib.stream_ptr(self.device))
+        st = run()
+        if st == -3 and self.n_per_graph > 0 and allow_general_fallback and int(self.array("status")[0].item()) == 8:
+            # the only complaint is an edge that crosses a sub-graph boundary: n_per_graph is a layout HINT for the
+            # shared-memory-tiled kernels, the reference accepts any batched edge_index -> use the general CSR kernels
+            self.n_per_graph = 0
+            st = run()
         _lib.check(st, "qagnn_graph_prep")
         self._keep = (ei, et, nt)
+
+    def combo_order(self):
+        """int32 [E+N]: by-source edge positions stably sorted by combo (for the backward's edge-table gradient)."""
+        if self._combo_order is None:
+            self._combo_order = torch.argsort(self.array("csr_src_combo"), stable=True).to(torch.int32)
+        return self._combo_order
+
+    def combo_count(self):
+        """int64 [C]: number of edges (self loops included) per combo index."""
+        return torch.bincount(self.array("combo").long(), minlength=self.R * self.T * self.T + self.T)
+
+    def status_word(self):
+        """Device-side error bits of the last qagnn_graph_prep on this buffer (0 = all indices in range)."""
+        return self.array("status")[0:1]
 
     def array(self, name):
         """int32 view of one prep array (tests / inspection)."""
@@ -101,6 +142,11 @@ class _FoldedWeights:
         self.key = None
         self.blob = None
         self._keep = None
+
+    def invalidate(self):
+        """Forget the folded blob.  Needed after parameter edits that bypass autograd's version counter
+        (`p.data.normal_()`, `bn.running_mean.data.fill_()`): the cache key is (data_ptr, _version, shape)."""
+        self.key = None
 
     def get(self, shape, enc, layers, mp_tensors, device):
         lib = _lib.load()
@@ -178,8 +224,14 @@ class GATConvE(nn.Module):
         """x [N, emb_dim]; edge_index [2, E]; edge_type [E]; node_type [N]; node_feature_extra [N, emb_dim].
         Returns out [N, emb_dim], or (out, (edge_index' [2,E+N], alpha [E+N, heads])) with
         return_attention_weights=True (alpha = softmax before the out-degree rescale, :473)."""
-        if self.training:
-            raise NotImplementedError("qagnn_b200.GATConvE implements the eval-mode forward only; call .eval()")
+        if self.training:  # dropout-free layer, BatchNorm batch statistics, autograd through the CUDA message passing
+            from . import training as TR
+            if prep is None:
+                prep = self._prep(edge_index, edge_type, node_type)
+            tab = TR.edge_table_train(self.edge_encoder, TR.combo_onehot_table(self.n_ntype, self.n_etype, x.device),
+                                      prep.combo_count(), 1)
+            return TR.gatconve_train(self, x, node_feature_extra, node_type, prep, tab, return_attention_weights)
+        _warn_if_grad_wanted("GATConvE", x, node_feature_extra)
         lib = _lib.load()
         xc = _lib.f32c(x, "x")
         ex = _lib.f32c(node_feature_extra, "node_feature_extra")
@@ -242,7 +294,21 @@ class QAGNN_Message_Passing(nn.Module):
         self.use_cuda_graph = False
         self._graphs = {}
         self._folded = _FoldedWeights()
-        self._ws = _DeviceBlob()
+        # a captured graph bakes in the workspace / folded-blob addresses: drop the graphs before either is replaced
+        self._ws = _DeviceBlob(on_replace=self._graphs.clear)
+        self._deferred_status = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self):
+        """Drops the folded weights and every captured CUDA graph.  Called automatically by load_state_dict() and
+        .to()/.cuda(); call it yourself after in-place edits through `.data` (e.g. `p.data.normal_()`, EMA swaps),
+        which do not bump the tensor version the caches are keyed on."""
+        self._folded.invalidate()
+        self._graphs.clear()
+
+    def _apply(self, fn, *a, **kw):
+        self.invalidate()
+        return super()._apply(fn, *a, **kw)
 
     # -- helpers ------------------------------------------------------------------------------
     def _shape(self, N, E, n_per_graph):
@@ -252,6 +318,21 @@ class QAGNN_Message_Passing(nn.Module):
     def _mp_tensors(self):
         return [self.emb_node_type.weight, self.emb_node_type.bias, self.emb_score.weight, self.emb_score.bias,
                 self.Vh.weight, self.Vh.bias, self.Vx.weight, self.Vx.bias, self._score_basis]
+
+    def _raise_deferred_status(self):
+        """CUDA-graph replays cannot synchronise to validate indices: every replay ORs graph prep's status word into a
+        device accumulator, which is copied to pinned memory asynchronously and inspected here once that copy has landed."""
+        if self._deferred_status is None:
+            return
+        host, ev, accum = self._deferred_status
+        if not ev.query():  # never block the host on the GPU here: the OR-accumulated word is looked at again later
+            return
+        self._deferred_status = None
+        if int(host.item()) != 0:
+            accum.zero_()
+            raise IndexError("qagnn_b200: the previous CUDA-graph replay saw edge_index / edge_type / node_type values out "
+                             f"of range or crossing a sub-graph boundary (status bits {int(host.item())}); its output was "
+                             "computed from clamped indices")
 
     def prepare_graph(self, edge_index, edge_type, node_type):
         """Builds the layer-invariant graph workspace; pass it back via forward(..., prep=) to amortise
@@ -288,9 +369,13 @@ class QAGNN_Message_Passing(nn.Module):
         node_score: tensor (batch_size, n_node, 1)
         returns (batch_size, n_node, d_node)
         """
-        if self.training:
-            raise NotImplementedError("qagnn_b200.QAGNN_Message_Passing implements the eval-mode forward only; "
-                                      "call .eval()")
+        self._raise_deferred_status()
+        if self.training:  # dropout, BatchNorm batch statistics, autograd through the CUDA message passing (training.py)
+            from . import training as TR
+            if prep is None:
+                prep = GraphPrep(A[0], A[1], node_type.reshape(-1), self.n_ntype, self.n_etype, 0, self.check_indices)
+            return TR.mp_forward_train(self, H, A, node_type, node_score, prep)
+        _warn_if_grad_wanted("QAGNN_Message_Passing", H, node_score)
         if self.use_cuda_graph and prep is None and not return_layers:
             return self._forward_graphed(H, A, node_type, node_score)
         lib = _lib.load()
@@ -305,7 +390,9 @@ class QAGNN_Message_Passing(nn.Module):
             raise ValueError("node_type / node_score must be [batch, n_node(, 1)]")
         edge_index, edge_type = A
         if prep is None:
-            prep = GraphPrep(edge_index, edge_type, nt, self.n_ntype, self.n_etype, n, self.check_indices)
+            prep = GraphPrep(edge_index, edge_type, nt, self.n_ntype, self.n_etype, n, self.check_indices,
+                             allow_general_fallback=True)
+        self._last_prep = prep
         if prep.N != B * n:
             raise ValueError("graph workspace was built for a different number of nodes")
         shape = self._shape(B * n, prep.E, prep.n_per_graph)
@@ -326,31 +413,40 @@ class QAGNN_Message_Passing(nn.Module):
 def _mp_forward_graphed(self, H, A, node_type, node_score):
     """CUDA-graph replay of forward() for inputs that live in the same device buffers as when it was captured."""
     tensors = [H, A[0], A[1], node_type, node_score]
-    key = (_version_key([t for t in self.parameters()] + [b for b in self.buffers()])[:0],
-           tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors),
-           tuple(p._version for p in self.parameters()))
+    key = (tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors),
+           _version_key(list(self.parameters()) + list(self.buffers())))
     entry = self._graphs.get(key)
     if entry is None:
         saved, self.use_cuda_graph = self.use_cuda_graph, False
         check, self.check_indices = self.check_indices, False
         try:
             if check:  # validate once, eagerly, before trusting the capture
-                GraphPrep(A[0], A[1], node_type, self.n_ntype, self.n_etype, node_type.size(1), True)
+                GraphPrep(A[0], A[1], node_type, self.n_ntype, self.n_etype, node_type.size(1), True,
+                          allow_general_fallback=True)
             side = torch.cuda.Stream(device=H.device)
             side.wait_stream(torch.cuda.current_stream(H.device))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: folds the weights, sizes the workspaces, sets kernel attributes
                     self.forward(H, A, node_type, node_score)
             torch.cuda.current_stream(H.device).wait_stream(side)
+            accum = torch.zeros(1, dtype=torch.int32, device=H.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self.forward(H, A, node_type, node_score)
+                accum.bitwise_or_(self._last_prep.status_word())
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[key] = (graph, out, tensors)
+            # the entry keeps alive everything whose address the graph baked in: inputs, workspace, folded blob, prep
+            entry = self._graphs[key] = (graph, out, tensors, self._ws.buf, self._folded.blob, self._last_prep, accum,
+                                         torch.zeros(1, dtype=torch.int32).pin_memory())
         finally:
             self.use_cuda_graph, self.check_indices = saved, check
     entry[0].replay()
+    if self.check_indices:  # later batches written into the same buffers: checked at the next call, without a sync here
+        entry[7].copy_(entry[6], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(H.device))
+        self._deferred_status = (entry[7], ev, entry[6])
     return entry[1]
 
 
@@ -408,7 +504,7 @@ class QAGNN(nn.Module):
         gnn_output = self.gnn(gnn_input, adj, node_type_ids, s)
         Z_vecs = gnn_output[:, 0]
         mask = (pos >= adj_lengths.unsqueeze(1)) | (node_type_ids == 3)
-        mask[mask.all(1), 0] = 0
+        mask[:, 0] = mask[:, 0] & ~mask.all(1)  # a fully masked row keeps node 0 (:176; written without a host sync)
         graph_vecs, pool_attn = self.pooler(sent_vecs, gnn_output, mask)
         if cache_output:
             self.concept_ids, self.adj, self.pool_attn = concept_ids, adj, pool_attn

@@ -150,8 +150,6 @@ def test_out_of_range_indices_raise():
     bad_t = d["edge_type"].clone(); bad_t[0] = 38
     with pytest.raises(IndexError):
         mod(d["H"], (d["edge_index"], bad_t), d["node_type"], d["node_score"])
-    with pytest.raises(NotImplementedError):
-        mod.train()(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
 
 
 # ---- full-size (BASELINE.json configs[1]) properties -----------------------------------------
@@ -225,6 +223,64 @@ def test_cross_graph_edge_is_rejected_when_n_per_graph_is_given():
     GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=0)  # legal for a general graph
     with pytest.raises(IndexError):
         GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=10)
+
+
+def test_cross_graph_edges_fall_back_to_the_general_kernels_in_the_module_api():
+    """n_per_graph is a layout hint: QAGNN_Message_Passing.forward accepts any batched edge_index like the reference
+    (ADVICE r1): an edge that crosses a sub-graph boundary routes the batch to the general CSR kernels."""
+    B, n, D, k = 3, 20, 64, 2
+    inp = O.synth_graph_batch(B, n, 50, D, 38, 9)
+    sd = O.random_state_dict(k, D, 4, 38, "peaky", 9)
+    ei = inp["edge_index"].clone()
+    ei[0, 0], ei[1, 0] = 1, n + 3            # graph 0 -> graph 1
+    ei[0, 1], ei[1, 1] = 2 * n + 5, 7        # graph 2 -> graph 0
+    ref = O.message_passing_forward(sd, inp["H"], ei, inp["edge_type"], inp["node_type"], inp["node_score"], k, 4, 38)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    d = _dev(inp)
+    out = mod(d["H"], (ei.to(DEV), d["edge_type"]), d["node_type"], d["node_score"])
+    assert mod._last_prep.n_per_graph == 0
+    Hh.assert_close(out, ref, "cross-graph batch vs oracle")
+
+
+# ---- the exact workload bench.py times (uniform synthetic batch, production-init weights, seed 100 + rank) ----------
+def test_bench_workload_matches_oracle_on_first_middle_and_last_graphs():
+    import bench
+    B, n, e, D, k = (bench.CFG[x] for x in ("graphs", "n", "e", "D", "k"))
+    inp = O.synth_graph_batch(B, n, e, D, bench.CFG["R"], seed=100)
+    sd = O.random_state_dict(k, D, bench.CFG["T"], bench.CFG["R"], "prod", seed=0)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, bench.CFG["T"], bench.CFG["R"], D, D, D).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    d = _dev(inp)
+    out = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"]).cpu()
+    # 36 graphs: the first 12, 12 from the middle, and the last 12 (the tail of the persistent kernel's last slot)
+    for g0 in (0, B // 2 - 6, B - 12):
+        ref = bench.oracle_slice(inp, sd, g0, 12)
+        Hh.assert_close(out[g0:g0 + 12], ref, f"bench workload graphs {g0}..{g0 + 11} vs oracle")
+    # the CUDA-graph replay bench.py times gives the same bits
+    mod.use_cuda_graph = True
+    rep = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"]).cpu()
+    assert torch.equal(rep, out)
+
+
+# ---- every launch-time switch the shipped library keeps (read at each call) has GPU coverage ------------------------
+@pytest.mark.parametrize("env", [{"QAGNN_MP_PATH": "csr"}, {"QAGNN_TC_2CTA": "0"}, {"QAGNN_GEMM": "ffma"},
+                                 {"QAGNN_MP_WARPS": "24"}, {"QAGNN_MP_WARPS": "31"}, {"QAGNN_MP_WARPS": "7"}])
+@pytest.mark.parametrize("name", ["cfg2small_peaky", "cfg2small_realistic", "tiny_realistic_d100", "no_edges"])
+def test_goldens_under_every_kept_switch(name, env, monkeypatch):
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sd = Hh.regen_mp_inputs(fx)
+    d = _dev(inp)
+    mod = _mp_module(c, fx, sd)
+    out, layers = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"], return_layers=True)
+    for l, ref_l in fx["layers"].items():
+        Hh.assert_close(layers[l], ref_l["x"], f"x[{l}] under {env}")
+    Hh.assert_close(out, fx["out"], f"out under {env}")
 
 
 def test_large_graph_general_path_matches_oracle():
@@ -329,9 +385,9 @@ def test_tiled_kernel_hub_nodes_and_unstaged_graphs():
     Hh.assert_close(out_c, ref_out, "out csr vs oracle")
 
 
-def test_fused_attention_pool_matches_torch_formulation():
+def test_fused_attention_pool_matches_oracle():
     """qagnn_attention_pool (keys/values folded into the query / out of the sum, one pass over the node tile) against
-    the reference formulation of MultiheadAttPoolLayer evaluated with torch ops on the CPU (utils/layers.py:344-371)."""
+    the oracle's restatement of MultiheadAttPoolLayer (utils/layers.py:324-371)."""
     from qagnn_b200.layers import MultiheadAttPoolLayer
     torch.manual_seed(3)
     for (b, n, D, S, nh) in [(7, 200, 200, 1024, 2), (3, 33, 64, 48, 4)]:
@@ -339,8 +395,9 @@ def test_fused_attention_pool_matches_torch_formulation():
         q, k = torch.randn(b, S), torch.randn(b, n, D) * 0.7
         mask = torch.rand(b, n) < 0.4
         mask[:, 0] = False
+        sd = {"pooler." + k_: v for k_, v in pool.state_dict().items()}
+        ref_out, ref_attn = O.multihead_att_pool(sd, "pooler", q, k, mask, nh)
         with torch.no_grad():
-            ref_out, ref_attn = pool(q, k, mask)            # CPU: einsum path
             got_out, got_attn = pool.to(DEV)(q.to(DEV), k.to(DEV), mask.to(DEV))  # CUDA: fused kernel
         Hh.assert_close(got_attn, ref_attn, "pool attn", atol=2e-6, rtol=1e-4)
         Hh.assert_close(got_out, ref_out, "pooled", atol=2e-5, rtol=1e-4)
@@ -369,10 +426,51 @@ def test_cuda_graph_replay_and_streamed_runner_match_plain_forward():
         if i >= 1:  # consume the previous result while this batch is in flight
             prev = (i - 1) % 2
             runner.ev_down[prev].synchronize()
-            got.append(runner.host_out[prev].clone())
+            got.append(runner.host_out[prev][0].clone())
     runner.drain()
     torch.cuda.synchronize()
-    got.append(runner.host_out[(len(host) - 1) % 2].clone())
+    got.append(runner.host_out[(len(host) - 1) % 2][0].clone())
     for a, b in zip(got, plain):
         assert torch.equal(a, b)
     assert len(mod._graphs) == 2  # one captured graph per buffer set
+
+
+def test_decoder_step_graph_matches_module_composition():
+    """qagnn_b200.pipeline.DecoderStep (MP forward + pool mask + fused pooling + answer MLP as ONE CUDA graph) gives the
+    same logits / attention as calling the decoder's modules one by one, and replays follow new contents of its buffers."""
+    from qagnn_b200.layers import MLP, MultiheadAttPoolLayer
+    from qagnn_b200.pipeline import DecoderStep
+    B, n, e, D, k, S = 10, 40, 120, 64, 2, 96
+    sd = O.random_state_dict(k, D, 4, 38, "peaky", 3)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    torch.manual_seed(4)
+    pooler = MultiheadAttPoolLayer(2, S, D).eval().to(DEV)
+    fc = MLP(D + S + D, D, 1, 0, 0.2, layer_norm=True).eval().to(DEV)
+
+    def batch(seed):
+        inp = O.synth_graph_batch(B, n, e, D, 38, seed, realistic=True)
+        inp["sent_vecs"] = torch.randn(B, S, generator=torch.Generator().manual_seed(seed)) * 0.5
+        return {k_: inp[k_].to(DEV) for k_ in DecoderStep.FIELDS}, inp
+
+    d, inp = batch(11)
+    step = DecoderStep(mod, pooler, fc, d, 1, None, use_cuda_graph=True)
+    assert step.graph is not None
+    for seed in (11, 12):
+        nd, ninp = batch(seed)
+        for k_ in DecoderStep.FIELDS:
+            d[k_].copy_(nd[k_])
+        logits, attn, gout = (t.clone() for t in step.run())
+        with torch.no_grad():
+            ref_out = O.message_passing_forward(sd, ninp["H"], ninp["edge_index"], ninp["edge_type"], ninp["node_type"],
+                                                ninp["node_score"], k, 4, 38)
+            mask = (torch.arange(n) >= ninp["adj_lengths"].unsqueeze(1)) | (ninp["node_type"] == 3)
+            mask[mask.all(1), 0] = 0
+            psd = {"pooler." + k_: v.cpu() for k_, v in pooler.state_dict().items()}
+            gv, ref_attn = O.multihead_att_pool(psd, "pooler", ninp["sent_vecs"], ref_out, mask, 2)
+            ref_logits = fc.cpu()(torch.cat((gv, ninp["sent_vecs"], ref_out[:, 0]), 1))
+            fc.to(DEV)
+        Hh.assert_close(gout, ref_out, f"gnn_out seed {seed}")
+        Hh.assert_close(attn, ref_attn, f"pool_attn seed {seed}", atol=2e-5)
+        Hh.assert_close(logits, ref_logits, f"logits seed {seed}")

@@ -1,0 +1,123 @@
+"""Training mode of the CUDA path: forward with BatchNorm batch statistics and the gradients of every
+parameter and input against goldens minted from the reference's own modules in .train() with autograd
+(oracle/make_goldens.py: mint_train_case; dropout 0 because a live mask stream cannot be reproduced).  Needs a GPU."""
+import pytest
+import torch
+
+import qagnn_b200
+from oracle import make_goldens as MG
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _module(fx, sd, dropout=0.0):
+    c = fx["case"]
+    mod = qagnn_b200.QAGNN_Message_Passing(None, c["k"], fx["n_ntype"], fx["n_etype"], c["D"], c["D"], c["D"], dropout=dropout)
+    mod.load_state_dict(sd, strict=True)
+    return mod.to(DEV)
+
+
+def _grad_close(got, ref, what):
+    # gradients span orders of magnitude across parameters: 1e-4 relative to the tensor's own scale, plus 1e-4 relative
+    scale = max(float(ref.abs().max()), 1e-6)
+    Hh.assert_close(got, ref, what, atol=1e-4 * scale, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", Hh.golden_names("train"))
+def test_training_forward_and_gradients_match_reference(name):
+    fx = Hh.load_golden(name)
+    c = fx["case"]
+    inp, sd = Hh.regen_mp_inputs(fx)
+    mod = _module(fx, sd).train()
+    H = inp["H"].to(DEV).requires_grad_(True)
+    score = inp["node_score"].to(DEV).requires_grad_(True)
+    out = mod(H, (inp["edge_index"].to(DEV), inp["edge_type"].to(DEV)), inp["node_type"].to(DEV), score)
+    Hh.assert_close(out, fx["out"], "train-mode out")
+    loss = (out * MG.train_loss_weights(c).to(DEV)).sum()
+    loss.backward()
+    assert abs(float(loss) - fx["loss"]) <= 1e-3 + 1e-4 * abs(fx["loss"])
+    _grad_close(H.grad, fx["grad_H"], "dL/dH")
+    _grad_close(score.grad, fx["grad_score"], "dL/dscore")
+    got = dict(mod.named_parameters())
+    assert sorted(got) == sorted(fx["grads"]), "parameter names (shared edge_encoder de-duplicated) differ from the reference"
+    for pname, ref_g in fx["grads"].items():
+        assert got[pname].grad is not None, pname
+        _grad_close(got[pname].grad, ref_g, f"dL/d{pname}")
+    bufs = dict(mod.named_buffers())
+    for bname, ref_b in fx["buffers_after"].items():
+        if "num_batches" in bname:
+            assert int(bufs[bname]) == int(ref_b), bname
+        else:
+            Hh.assert_close(bufs[bname], ref_b, bname, atol=1e-5, rtol=1e-4)
+
+
+def test_train_then_eval_uses_updated_weights_and_statistics():
+    """An optimiser step and the BatchNorm running-statistics update must invalidate the folded eval-mode weights."""
+    fx = Hh.load_golden("train_cfg1_peaky_k2")
+    inp, sd = Hh.regen_mp_inputs(fx)
+    mod = _module(fx, sd)
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    args = (d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    before = mod.eval()(*args).clone()
+    opt = torch.optim.SGD(mod.parameters(), lr=0.05)
+    out = mod.train()(*args)
+    out.square().mean().backward()
+    opt.step()
+    after = mod.eval()(*args)
+    assert not torch.allclose(before, after, atol=1e-4), "eval output did not change after a training step"
+    # the same weights loaded into a fresh module give the same eval output (nothing stale in the folded cache)
+    fresh = _module(fx, {k: v.detach().cpu() for k, v in mod.state_dict().items()}).eval()
+    Hh.assert_close(after, fresh(*args).cpu(), "eval after step vs fresh module", atol=1e-6, rtol=1e-6)
+    # .data edits do not bump the version counter: invalidate() is the documented way
+    with torch.no_grad():
+        mod.Vh.weight.data.mul_(0.5)
+    mod.invalidate()
+    fresh2 = _module(fx, {k: v.detach().cpu() for k, v in mod.state_dict().items()}).eval()
+    Hh.assert_close(mod(*args), fresh2(*args).cpu(), "eval after .data edit + invalidate()", atol=1e-6, rtol=1e-6)
+
+
+def test_dropout_is_applied_in_training_mode_only():
+    fx = Hh.load_golden("train_cfg1_peaky_k2")
+    inp, sd = Hh.regen_mp_inputs(fx)
+    mod = _module(fx, sd, dropout=0.5).train()
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    args = (d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    torch.manual_seed(0)
+    a = mod(*args)
+    b = mod(*args)
+    zero_frac = float((a == 0).float().mean())
+    assert 0.4 < zero_frac < 0.6, f"final dropout (modeling_qagnn.py:93) should zero ~half of the outputs, got {zero_frac}"
+    assert not torch.equal(a, b), "two training-mode forwards must draw different dropout masks"
+    e1, e2 = mod.eval()(*args), mod.eval()(*args)
+    assert torch.equal(e1, e2) and float((e1 == 0).float().mean()) < 0.01
+
+
+def test_single_layer_training_gradients_against_autograd_of_the_oracle():
+    """GATConvE alone in .train(): gradients of x / extra / weights vs autograd through the CPU oracle's op-for-op
+    restatement with batch statistics (the oracle is differentiable: it is written in torch ops)."""
+    from oracle import qagnn_oracle as O
+    D, Hd, T, R = 64, 4, 4, 38
+    inp = O.synth_graph_batch(3, 30, 90, D, R, seed=31)
+    sd = O.random_state_dict(1, D, T, R, "peaky", seed=31)
+    x = inp["H"].view(-1, D).clone().requires_grad_(True)
+    g0 = torch.Generator().manual_seed(5)
+    extra = (torch.randn(x.shape, generator=g0) * 0.5).requires_grad_(True)
+    nt = inp["node_type"].view(-1)
+    ref_out, _, ref_alpha, _ = O.gatconve_forward(sd, "gnn_layers.0", x, inp["edge_index"], inp["edge_type"], nt, extra, T, R,
+                                                  head_count=Hd, train=True)
+    G = torch.randn(ref_out.shape, generator=g0)
+    (ref_out * G).sum().backward()
+    enc = torch.nn.Sequential(torch.nn.Linear(R + 1 + 2 * T, D), torch.nn.BatchNorm1d(D), torch.nn.ReLU(), torch.nn.Linear(D, D))
+    layer = qagnn_b200.GATConvE(None, D, T, R, enc, head_count=Hd)
+    layer.load_state_dict({k_[len("gnn_layers.0."):]: v for k_, v in sd.items() if k_.startswith("gnn_layers.0.")})
+    layer = layer.to(DEV).train()
+    xg = x.detach().to(DEV).requires_grad_(True)
+    eg = extra.detach().to(DEV).requires_grad_(True)
+    out, (_, alpha) = layer(xg, inp["edge_index"].to(DEV), inp["edge_type"].to(DEV), nt.to(DEV), eg, return_attention_weights=True)
+    Hh.assert_close(out, ref_out.detach(), "train-mode GATConvE out")
+    Hh.assert_close(alpha, ref_alpha.detach(), "alpha")
+    (out * G.to(DEV)).sum().backward()
+    _grad_close(xg.grad, x.grad, "dL/dx")
+    _grad_close(eg.grad, extra.grad, "dL/dextra")
