@@ -17,13 +17,18 @@ import torch
 @dataclass
 class PackedAdj:
     """edge_index int64 [2, total_E] with per-graph node offsets already applied, edge_type int64 [total_E],
-    graph_ptr int64 [n_graphs + 1] = first edge of each graph."""
+    graph_ptr int64 [n_graphs + 1] = first edge of each graph.  When built by FlatAdjCache.pack the two tensors are views
+    of ONE [3, total_E] buffer (`buf`), so the whole adjacency of a batch moves to the device in a single copy."""
     edge_index: torch.Tensor
     edge_type: torch.Tensor
     graph_ptr: torch.Tensor
     n_nodes: int
+    buf: torch.Tensor = None
 
     def to(self, device, non_blocking=True):
+        if self.buf is not None:
+            b = self.buf.to(device, non_blocking=non_blocking)
+            return PackedAdj(b[:2], b[2], self.graph_ptr, self.n_nodes, b)
         return PackedAdj(self.edge_index.to(device, non_blocking=non_blocking),
                          self.edge_type.to(device, non_blocking=non_blocking), self.graph_ptr, self.n_nodes)
 
@@ -158,3 +163,140 @@ def synth_adj_pickle(path, n_records, seed=0, n_rel=17, max_nodes=400):
     with open(path, "wb") as f:
         pickle.dump(records, f)
     return records
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Flat adjacency cache + pre-packed batch generator
+# ------------------------------------------------------------------------------------------------------------------
+class FlatAdjCache:
+    """All sub-graphs of a split as three flat arrays + a row pointer (a CSR over graphs), instead of the reference's
+    [n_samples][num_choice] nested lists of small tensors (utils/data_utils.py:174-190):
+
+        src, tgt int32 [total_E] (LOCAL node ids), etype int16 [total_E], graph_ptr int64 [n_graphs + 1]
+
+    Written once next to the reference's `.loaded_cache` as `<adj_pk_path>.flat_cache.npz` and memory-mapped afterwards;
+    `pack(graph_ids)` cuts a batch out of it with three vectorised gathers into ONE pinned [3, E] int64 buffer."""
+
+    def __init__(self, src, tgt, etype, graph_ptr, num_choice, n_nodes):
+        self.src, self.tgt, self.etype, self.graph_ptr = src, tgt, etype, graph_ptr
+        self.num_choice, self.n_nodes = int(num_choice), int(n_nodes)
+
+    @classmethod
+    def from_nested(cls, edge_index_nested, edge_type_nested, n_nodes):
+        flat_ei = [e for row in edge_index_nested for e in row]
+        flat_et = [e for row in edge_type_nested for e in row]
+        counts = np.array([e.size(1) for e in flat_ei], dtype=np.int64)
+        ptr = np.zeros(len(flat_ei) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(counts)
+        if int(ptr[-1]):
+            ei = torch.cat(flat_ei, dim=1).numpy()
+            et = torch.cat(flat_et, dim=0).numpy()
+        else:
+            ei, et = np.zeros((2, 0), np.int64), np.zeros((0,), np.int64)
+        return cls(ei[0].astype(np.int32), ei[1].astype(np.int32), et.astype(np.int16), ptr, len(edge_index_nested[0]), n_nodes)
+
+    def save(self, path):
+        np.savez(path, src=self.src, tgt=self.tgt, etype=self.etype, graph_ptr=self.graph_ptr,
+                 meta=np.array([self.num_choice, self.n_nodes], dtype=np.int64))
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, mmap_mode="r")
+        meta = z["meta"]
+        return cls(z["src"], z["tgt"], z["etype"], z["graph_ptr"], int(meta[0]), int(meta[1]))
+
+    def n_graphs(self):
+        return len(self.graph_ptr) - 1
+
+    def pack(self, question_indexes, pin=True):
+        """PackedAdj of the questions `question_indexes` (all their choices, in order) — equal to
+        LM_QAGNN.batch_graph applied to the corresponding nested-list slice (modeling_qagnn.py:244-251)."""
+        q = np.asarray(question_indexes, dtype=np.int64).reshape(-1)
+        gids = (q[:, None] * self.num_choice + np.arange(self.num_choice)[None, :]).reshape(-1)
+        beg, end = self.graph_ptr[gids], self.graph_ptr[gids + 1]
+        counts = end - beg
+        ptr = np.zeros(len(gids) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum(counts)
+        total = int(ptr[-1])
+        # flat positions of every edge of the batch: beg[g] + (0 .. counts[g]-1)
+        pos = np.repeat(beg - ptr[:-1], counts) + np.arange(total, dtype=np.int64)
+        off = np.repeat(np.arange(len(gids), dtype=np.int64) * self.n_nodes, counts)
+        buf = torch.empty(3, total, dtype=torch.long, pin_memory=pin and torch.cuda.is_available())
+        b = buf.numpy()
+        np.add(self.src[pos], off, out=b[0], casting="unsafe")
+        np.add(self.tgt[pos], off, out=b[1], casting="unsafe")
+        b[2] = self.etype[pos]
+        return PackedAdj(buf[:2], buf[2], torch.from_numpy(ptr), self.n_nodes, buf)
+
+
+def load_flat_adj_cache(adj_pk_path, max_node_num, num_choice, args=None):
+    """(concept_ids, node_type_ids, node_scores, adj_lengths, FlatAdjCache): the loader above with the adjacency as a flat
+    cache; `<adj_pk_path>.flat_cache.npz` is written on first use and memory-mapped on later ones."""
+    flat_path = adj_pk_path + ".flat_cache.npz"
+    cids, ntypes, scores, lens, (ei, et) = load_sparse_adj_data_with_contextnode(adj_pk_path, max_node_num, num_choice, args)
+    if os.path.exists(flat_path):
+        flat = FlatAdjCache.load(flat_path)
+        if flat.n_graphs() == cids.size(0) * num_choice and flat.n_nodes == max_node_num and flat.num_choice == num_choice:
+            return cids, ntypes, scores, lens, flat
+    flat = FlatAdjCache.from_nested(ei, et, max_node_num)
+    flat.save(flat_path)
+    return cids, ntypes, scores, lens, flat
+
+
+class PackedAdjBatchGenerator:
+    """Drop-in for the reference's MultiGPUSparseAdjDataBatchGenerator (utils/data_utils.py:17-76): same constructor, same
+    batch tuple  (qids, labels, *tensors0, *lists0, *tensors1, *lists1, edge_index, edge_type),  same partial-batch
+    options — but `adj_data` may be a FlatAdjCache, in which case the adjacency of a batch is packed on the host into one
+    pinned buffer and moved with ONE non-blocking copy; the `edge_index` slot then holds a PackedAdj (which
+    LM_QAGNN.forward accepts) and the `edge_type` slot its edge_type view.  Tensors are staged through pinned memory as
+    well, so every copy of a batch is asynchronous.  With nested-list `adj_data` it behaves exactly like the reference."""
+
+    def __init__(self, args, mode, device0, device1, batch_size, indexes, qids, labels, tensors0=[], lists0=[], tensors1=[],
+                 lists1=[], adj_data=None):
+        self.args, self.mode = args, mode
+        self.device0, self.device1 = device0, device1
+        self.batch_size, self.indexes, self.qids, self.labels = batch_size, indexes, qids, labels
+        self.tensors0, self.lists0, self.tensors1, self.lists1 = tensors0, lists0, tensors1, lists1
+        self.adj_data = adj_data
+
+    def __len__(self):
+        return (self.indexes.size(0) - 1) // self.batch_size + 1
+
+    def _to_device(self, obj, device):
+        if isinstance(obj, (tuple, list)):
+            return [self._to_device(item, device) for item in obj]
+        if isinstance(obj, PackedAdj):
+            return obj.to(device, non_blocking=True)
+        if torch.cuda.is_available() and torch.device(device).type == "cuda" and not obj.is_pinned():
+            obj = obj.pin_memory()
+        return obj.to(device, non_blocking=True)
+
+    def __iter__(self):
+        bs = self.batch_size
+        n = self.indexes.size(0)
+        if self.mode == "train" and getattr(self.args, "drop_partial_batch", False):
+            n = (n // bs) * bs
+        elif self.mode == "train" and getattr(self.args, "fill_partial_batch", False):
+            remain = n % bs
+            if remain > 0:
+                extra = np.random.choice(self.indexes[:-remain], size=(bs - remain), replace=False)
+                self.indexes = torch.cat([self.indexes, torch.tensor(extra)])
+                n = self.indexes.size(0)
+        for a in range(0, n, bs):
+            b = min(n, a + bs)
+            batch_indexes = self.indexes[a:b]
+            batch_qids = [self.qids[idx] for idx in batch_indexes]
+            batch_labels = self._to_device(self.labels[batch_indexes], self.device1)
+            batch_tensors0 = [self._to_device(x[batch_indexes], self.device0) for x in self.tensors0]
+            batch_tensors1 = [self._to_device(x[batch_indexes], self.device1) for x in self.tensors1]
+            batch_lists0 = [self._to_device([x[i] for i in batch_indexes], self.device0) for x in self.lists0]
+            batch_lists1 = [self._to_device([x[i] for i in batch_indexes], self.device1) for x in self.lists1]
+            if isinstance(self.adj_data, FlatAdjCache):
+                packed = self._to_device(self.adj_data.pack(batch_indexes.numpy()), self.device1)
+                edge_index, edge_type = packed, packed.edge_type
+            else:
+                edge_index_all, edge_type_all = self.adj_data
+                edge_index = self._to_device([edge_index_all[i] for i in batch_indexes], self.device1)
+                edge_type = self._to_device([edge_type_all[i] for i in batch_indexes], self.device1)
+            yield tuple([batch_qids, batch_labels, *batch_tensors0, *batch_lists0, *batch_tensors1, *batch_lists1,
+                         edge_index, edge_type])

@@ -56,3 +56,66 @@ def test_loader_invariants_and_packing(tmp_path):
             assert torch.equal(e[:, half:], e[:, :half].flip(0)) and torch.equal(t[half:], t[:half] + 19)
     packed = Dt.pack_adj(ei, et, n, pin=False)
     assert packed.edge_index.shape[1] == sum(x.shape[1] for r in ei for x in r)
+
+
+def _make_split(tmp_path, n_records=30, n=40, nc=5):
+    path = str(tmp_path / "s.graph.adj.pk")
+    Dt.synth_adj_pickle(path, n_records, seed=2, max_nodes=60)
+    return path, Dt.load_sparse_adj_data_with_contextnode(path, n, nc, None, use_cache=False, write_cache=False)
+
+
+def test_flat_cache_pack_equals_batch_graph_of_the_nested_lists(tmp_path):
+    n, nc = 40, 5
+    path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 30, n, nc)
+    flat = Dt.FlatAdjCache.from_nested(ei, et, n)
+    flat.save(path + ".flat_cache.npz")
+    flat2 = Dt.FlatAdjCache.load(path + ".flat_cache.npz")
+    for idx in ([0, 1, 2], [5, 1, 3, 3], [4]):
+        want = Dt.pack_adj([ei[i] for i in idx], [et[i] for i in idx], n, pin=False)
+        for f in (flat, flat2):
+            got = f.pack(idx, pin=False)
+            assert torch.equal(got.edge_index, want.edge_index) and torch.equal(got.edge_type, want.edge_type)
+            assert torch.equal(got.graph_ptr, want.graph_ptr)
+            assert got.buf.data_ptr() == got.edge_index.data_ptr()  # one buffer: one host-to-device copy
+    # load_flat_adj_cache writes the file once and reuses it
+    out = Dt.load_flat_adj_cache(path, n, nc)
+    assert isinstance(out[4], Dt.FlatAdjCache) and out[4].n_graphs() == cids.size(0) * nc
+    assert torch.equal(out[4].pack([1]).edge_index, Dt.pack_adj([ei[1]], [et[1]], n, pin=False).edge_index)
+
+
+def test_packed_batch_generator_matches_reference_generator(tmp_path):
+    n, nc, bs = 40, 5, 4
+    path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 50, n, nc)  # 10 questions
+    Q = cids.size(0)
+    qids = [f"q{i}" for i in range(Q)]
+    labels = torch.arange(Q) % nc
+    lm = torch.arange(Q * nc * 7).view(Q, nc, 7)
+    indexes = torch.randperm(Q, generator=torch.Generator().manual_seed(0))
+
+    class Args:
+        drop_partial_batch = False
+        fill_partial_batch = False
+    kw = dict(tensors0=[lm], tensors1=[cids, ntypes, scores, lens])
+    flat = Dt.FlatAdjCache.from_nested(ei, et, n)
+    ours = list(Dt.PackedAdjBatchGenerator(Args(), "eval", "cpu", "cpu", bs, indexes, qids, labels, adj_data=flat, **kw))
+    nested = list(Dt.PackedAdjBatchGenerator(Args(), "eval", "cpu", "cpu", bs, indexes, qids, labels, adj_data=(ei, et), **kw))
+    ref = nested
+    if os.path.isdir(os.path.join(REF, "utils")):  # build container: the reference's own generator
+        sys.path.insert(0, REF)
+        try:
+            from oracle.ref_shim import _install_stubs
+            _install_stubs()
+            from utils import data_utils as RD
+            ref = list(RD.MultiGPUSparseAdjDataBatchGenerator(Args(), "eval", "cpu", "cpu", bs, indexes, qids, labels,
+                                                              adj_data=(ei, et), **kw))
+        finally:
+            sys.path.remove(REF)
+    assert len(ours) == len(ref) == len(nested) == (Q + bs - 1) // bs
+    for bo, bn, br in zip(ours, nested, ref):
+        assert bo[0] == br[0] == bn[0] and torch.equal(bo[1], br[1])
+        for x, y, z in zip(bo[2:-2], br[2:-2], bn[2:-2]):
+            assert torch.equal(x, y) and torch.equal(z, y)
+        assert _equal_nested(bn[-2], br[-2]) and _equal_nested(bn[-1], br[-1])
+        want = Dt.pack_adj(br[-2], br[-1], n, pin=False)  # == LM_QAGNN.batch_graph of the reference's nested batch
+        assert isinstance(bo[-2], Dt.PackedAdj)
+        assert torch.equal(bo[-2].edge_index, want.edge_index) and torch.equal(bo[-1], want.edge_type)
