@@ -211,6 +211,14 @@ int32_t qagnn_attention_pool(int32_t B, int32_t n, int32_t D, int32_t n_head, co
                              const uint8_t *mask, const float *wk, const float *bk, const float *wv, const float *bv,
                              float *pooled, float *attn, void *stream);
 
+/* The step before the path: QAGNN.forward's input assembly (modeling_qagnn.py:153-167), eval mode, one kernel:
+ *   H_out[b,0,:] = ctx[b,:] (= GELU(svec2nvec(sent_vecs)), caller-computed [B,D]);  H_out[b,i,:] = table[concept_ids[b,i]-1], i >= 1,
+ *   with `table` [n_concept, D] the concept embedding after cpt_transform + GELU (folded once by the caller; the table is
+ *   frozen in eval);  scores_out [B,n] = the reference's relevance-score normalisation of node_scores [B,n] by adj_lengths. */
+int32_t qagnn_decoder_head(int32_t B, int32_t n, int32_t D, const int64_t *concept_ids, int64_t n_concept, const float *table,
+                           const float *ctx, const float *node_scores, const int64_t *adj_lengths, float *H_out,
+                           float *scores_out, void *stream);
+
 /* Launch counters since load (kernels this library enqueued); for bench.py's gpu_launches. */
 int64_t qagnn_launch_count(void);
 

@@ -151,6 +151,23 @@ class CustomizedEmbedding(nn.Module):
                     raise
         return self.activation(lin(e))
 
+    def projected_table(self):
+        """[concept_num, concept_out_dim] = the whole table pushed through scale / cpt_transform / GELU, cached per weight
+        version (eval mode: the embedding is frozen and the projection fixed, so a forward becomes a pure row gather).
+        `invalidate_table()` after in-place `.data` edits."""
+        srcs = [self.emb.weight] + ([self.cpt_transform.weight, self.cpt_transform.bias] if hasattr(self, "cpt_transform") else [])
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+        if getattr(self, "_ptab_key", None) != key:
+            with torch.no_grad():
+                w = self.emb.weight
+                rows = [self._project(w[i:i + 65536]) for i in range(0, w.size(0), 65536)]  # chunks bound the GEMM workspace
+                self._ptab = torch.cat(rows).contiguous()
+            self._ptab_key = key
+        return self._ptab
+
+    def invalidate_table(self):
+        self._ptab_key = None
+
     def forward(self, index, contextualized_emb=None):
         if contextualized_emb is not None:
             if index.size(0) != contextualized_emb.size(0):

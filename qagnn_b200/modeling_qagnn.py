@@ -489,17 +489,37 @@ class QAGNN(nn.Module):
                         cache_output=False):
         """Everything up to (and excluding) the answer MLP: returns (concat [B, 2*concept_dim+sent_dim], pool_attn).
         Split out so a data-parallel caller can all-gather `concat` before `fc` (qagnn_b200.distributed)."""
-        gnn_input0 = self.activation(self.svec2nvec(sent_vecs)).unsqueeze(1)
-        gnn_input1 = self.concept_emb(concept_ids[:, 1:] - 1, emb_data).to(node_type_ids.device)
-        gnn_input = self.dropout_e(torch.cat([gnn_input0, gnn_input1], dim=1))
-
         n = node_scores.size(1)
         pos = torch.arange(n, device=node_scores.device)
-        valid = (pos < adj_lengths.unsqueeze(1)).float()
-        s = -node_scores
-        s = (s - s[:, 0:1, :]).squeeze(2) * valid
-        mean_norm = s.abs().sum(dim=1) / adj_lengths
-        s = (s / (mean_norm.unsqueeze(1) + 1e-05)).unsqueeze(2)
+        fused_head = (not self.training and not torch.is_grad_enabled() and emb_data is None and node_scores.is_cuda
+                      and not self.concept_emb.use_contextualized and self.concept_dim % 4 == 0
+                      and concept_ids.device == node_scores.device and sent_vecs.dtype == torch.float32)
+        if fused_head:
+            # one kernel: context-node injection + concept rows gathered from the pre-projected table + score
+            # normalisation (:153-167); the [B, sent_dim] svec2nvec GEMM stays a library call
+            lib = _lib.load()
+            B_ = concept_ids.size(0)
+            table = self.concept_emb.projected_table()
+            ctx = self.activation(self.svec2nvec(sent_vecs)).contiguous()
+            cid = _lib.i64c(concept_ids, "concept_ids")
+            sc = _lib.f32c(node_scores.reshape(B_, n), "node_scores")
+            al = _lib.i64c(adj_lengths, "adj_lengths")
+            gnn_input = torch.empty(B_, n, self.concept_dim, dtype=torch.float32, device=sc.device)
+            s = torch.empty(B_, n, dtype=torch.float32, device=sc.device)
+            with torch.cuda.device(sc.device):
+                st = lib.qagnn_decoder_head(B_, n, self.concept_dim, _lib.ptr(cid), table.size(0), _lib.ptr(table), _lib.ptr(ctx),
+                                            _lib.ptr(sc), _lib.ptr(al), _lib.ptr(gnn_input), _lib.ptr(s), _lib.stream_ptr(sc.device))
+            _lib.check(st, "qagnn_decoder_head")
+            s = s.unsqueeze(2)
+        else:
+            gnn_input0 = self.activation(self.svec2nvec(sent_vecs)).unsqueeze(1)
+            gnn_input1 = self.concept_emb(concept_ids[:, 1:] - 1, emb_data).to(node_type_ids.device)
+            gnn_input = self.dropout_e(torch.cat([gnn_input0, gnn_input1], dim=1))
+            valid = (pos < adj_lengths.unsqueeze(1)).float()
+            s = -node_scores
+            s = (s - s[:, 0:1, :]).squeeze(2) * valid
+            mean_norm = s.abs().sum(dim=1) / adj_lengths
+            s = (s / (mean_norm.unsqueeze(1) + 1e-05)).unsqueeze(2)
 
         gnn_output = self.gnn(gnn_input, adj, node_type_ids, s)
         Z_vecs = gnn_output[:, 0]
