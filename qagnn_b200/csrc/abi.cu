@@ -71,6 +71,8 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   W.xp_hi[1] = take(half); W.xp_lo[1] = take(half);
   W.ap_hi = take(half); W.ap_lo = take(half);
   W.mp_hi = take(half); W.mp_lo = take(half);
+  const size_t sbh = N * (size_t)round_up8((int)(D / 2)) / 2 + 8;  // one bf16 plane [N, KSh], in floats
+  W.sb_hi = take(sbh); W.sb_lo = take(sbh);
   const size_t Eps = (Ep + 3) / 4 * 4;  // per-head stride of the tiled path
   W.score = take(Eps * H);
   W.alpha = take(Eps * H);
@@ -95,6 +97,24 @@ __global__ void node_feature_prologue_kernel(int64_t N, int D, int T, const int6
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
     extra[v * D + j] = type_tab[t * Dh + j];
     sinb[i] = sinf(basis[j] * node_score[v]);  // precise sinf: arguments reach ~1e4 * |score|
+  }
+}
+
+// sin basis of the relevance score as split-bf16 planes [N, ld]: the A operand of emb_score on the tensor-core path (:70-73)
+__global__ void sin_basis_planes_kernel(int64_t N, int Dh, int ld, const float* __restrict__ node_score,
+                                        const float* __restrict__ basis, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo) {
+  const int half = Dh / 2;  // Dh even: two columns per thread
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * half; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / half;
+    const int j = (int)(i % half) * 2;
+    const float sc = node_score[v];
+    const float a = sinf(basis[j] * sc), b = sinf(basis[j + 1] * sc);  // precise sinf: arguments reach ~1e4 * |score|
+    __nv_bfloat162 h2, l2;
+    h2.x = __float2bfloat16_rn(a); h2.y = __float2bfloat16_rn(b);
+    l2.x = __float2bfloat16_rn(a - __bfloat162float(h2.x)); l2.y = __float2bfloat16_rn(b - __bfloat162float(h2.y));
+    *reinterpret_cast<__nv_bfloat162*>(hi + v * ld + j) = h2;
+    *reinterpret_cast<__nv_bfloat162*>(lo + v * ld + j) = l2;
   }
 }
 
@@ -235,7 +255,7 @@ struct Planes {
 int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, int layer, Planes x, Planes extra,
                          const void* prep, const qagnn_prep_layout& pl, const float* folded, float* out_f32,
                          void* out_hi, void* out_lo, float* alpha_out, float* aggr_out, float* ws, Act final_act,
-                         bool tiled, cudaStream_t st) {
+                         bool tiled, cudaStream_t st, const int64_t* type_bias_classes = nullptr) {
   const int D = s.D;
   const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
   float* qkm = ws + W.qkm;
@@ -245,7 +265,17 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
     ProfScope ps(QAGNN_PROF_PROJECTION, st);
     TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D};
     TcOutput o{};
-    if (tiled) {  // per-head padded weight rows -> the GEMM writes [3][H][N][DP] (pads = exact zeros) itself
+    if (tiled && type_bias_classes != nullptr) {
+      // fast form (qagnn_mp_forward): `extra` holds only score_emb (K = D/2); the type-embedding half of node_feature_extra
+      // enters as a per-node-type bias row (T distinct rows), so the GEMM runs K = D + D/2 instead of 2D
+      const int DP = head_dim_padded(D / s.H), KS = round_up8(D + D / 2);
+      TcOperand A2s{extra.hi, extra.lo, D, D / 2};
+      TcOperand Wp{lb + L.wps_hi, lb + L.wps_lo, KS, D + D / 2};
+      o.hm_buf = qkm;
+      o.hm = HeadMajorOut{1, D, D / s.H, DP, s.H};
+      o.row_class = type_bias_classes; o.class_stride = 3 * s.H * DP; o.n_class = s.T;
+      QAGNN_RETURN_IF(gemm_tc(A1, A2s, Wp, lb + L.tbias, s.N, 3 * s.H * DP, ACT_NONE, o, st));
+    } else if (tiled) {  // per-head padded weight rows -> the GEMM writes [3][H][N][DP] (pads = exact zeros) itself
       const int DP = head_dim_padded(D / s.H);
       TcOperand Wp{lb + L.wph_hi, lb + L.wph_lo, 2 * D, 2 * D};
       o.hm_buf = qkm;
@@ -419,10 +449,29 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   const float* f = (const float*)folded;
   float* extra = ws + W.extra;
   const bool tc = use_tc(s);
-  // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
-  QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
-                                tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
   const bool tiled = use_headtile(s);
+  // fast form: tensor-core emb_score + type-embedding half of node_feature_extra folded into per-type bias rows
+  // (QAGNN_MP_FASTPROJ=0 keeps the general [x | extra] projection, for A/B runs and tests)
+  const char* efp = getenv("QAGNN_MP_FASTPROJ");
+  const bool fast = tc && tiled && s.k > 0 && (s.D / 2) % 2 == 0 && !(efp && atoi(efp) == 0);
+  if (fast) {
+    ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
+    const int Dh = s.D / 2, KSh = round_up8(Dh);
+    int64_t g = (s.N * (Dh / 2) + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    sin_basis_planes_kernel<<<(unsigned)g, 256, 0, st>>>(s.N, Dh, KSh, node_score, f + L.basis, (__nv_bfloat16*)(ws + W.sb_hi),
+                                                         (__nv_bfloat16*)(ws + W.sb_lo));
+    QAGNN_CHECK_LAUNCH();
+    // score_emb = GELU(emb_score(sin basis)) -> columns [0, D/2) of the `extra` planes               (:73)
+    TcOperand A{ws + W.sb_hi, ws + W.sb_lo, KSh, Dh}, none{nullptr, nullptr, 0, 0}, Wsc{f + L.ws_hi, f + L.ws_lo, KSh, Dh};
+    TcOutput o{};
+    o.hi = ws + W.ep_hi; o.lo = ws + W.ep_lo; o.ldp = s.D;
+    QAGNN_RETURN_IF(gemm_tc(A, none, Wsc, f + L.bs, s.N, Dh, ACT_GELU, o, st));
+  } else {
+    // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
+    QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
+                                  tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
+  }
   if (tiled && !use_tc(s)) QAGNN_RETURN_IF(zero_head_pads(s, ws + W.qkm, st));
   const size_t ND = (size_t)s.N * s.D;
   if (tc) {
@@ -438,7 +487,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
       void* ohi = ws + W.xp_hi[l & 1];
       void* olo = ws + W.xp_lo[l & 1];
       QAGNN_RETURN_IF(layer_forward_tc(s, L, W, l, xin, ep, prep, pl, f, xo32, ohi, olo, nullptr, nullptr, ws, ACT_GELU,
-                                       tiled, st));
+                                       tiled, st, fast ? node_type : nullptr));
       xin = Planes{ohi, olo};
     }
     // output = GELU(Vh(H) + Vx(X))                                           (:92)

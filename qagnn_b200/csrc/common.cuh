@@ -84,6 +84,12 @@ struct FoldLayout {
   size_t w1_hi, w1_lo;   // [D, D]
   size_t w2_hi, w2_lo;   // [D, D]
   size_t vcat_hi, vcat_lo;  // [D, 2D]  (global, not per layer)
+  // fast projection of qagnn_mp_forward (tiled + tensor-core path): node_feature_extra = [type_emb | score_emb] and type_emb
+  // has only T distinct rows, so its half of the projection is a per-node-type bias table and K shrinks from 2D to D + D/2
+  size_t ws_hi, ws_lo;   // global: emb_score.weight planes [D/2, KSh] (KSh = D/2 rounded up to 8)
+  size_t wps;            // per layer fp32 [3*H*DP, KS]: [x columns | score_emb columns] of wph (KS = D + D/2 rounded up to 8)
+  size_t wps_hi, wps_lo; // its planes
+  size_t tbias;          // per layer [T, 3*H*DP]: bph + wph[:, D:D+D/2] . type_tab[t]
   size_t total;      // floats
 };
 FoldLayout make_fold_layout(const qagnn_shape& s);
@@ -102,6 +108,7 @@ struct WorkLayout {
   size_t xp_hi[2], xp_lo[2];    // layer activations, ping-pong
   size_t ap_hi, ap_lo;          // aggr
   size_t mp_hi, mp_lo;          // mlp hidden
+  size_t sb_hi, sb_lo;          // sin basis [N, KSh] planes (A operand of emb_score on the tensor-core path)
   size_t score;   // [E', H]  raw logits / exp scratch (by-source order)
   size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order; general CSR path)
   size_t alpha2;  // [H, E'] x 2 words  tiled path: {row offsets, a'} per edge and head in by-target order
@@ -137,6 +144,8 @@ struct TcOutput {
   float* f32; int ldc;
   float* hm_buf; HeadMajorOut hm;
   void* hi; void* lo; int ldp;
+  // optional per-row bias tables: bias becomes bias[row_class[r] * class_stride + column], classes clamped to [0, n_class)
+  const int64_t* row_class; int class_stride; int n_class;
 };
 bool gemm_tc_available();
 bool gemm_tc_shape_ok(int K1, int K2, int lda1, int lda2, int ldw, int N);
@@ -146,6 +155,7 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
 
 // ---- shared-memory-tiled message passing (mp_headtile.cu) ----------------------------------------------
 inline int head_dim_padded(int d) { return (d + 3) / 4 * 4; }
+inline int round_up8(int k) { return (k + 7) / 8 * 8; }
 // true when the per-head persistent kernel can run this shape on this device
 bool headtile_supported(const qagnn_shape& s);
 int32_t launch_message_passing_headtile(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,

@@ -30,6 +30,9 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   L.vbias = take(D);
   L.vcat_hi = take(D * 2 * D / 2);
   L.vcat_lo = take(D * 2 * D / 2);
+  const size_t KSh = (size_t)round_up8((int)Dh), KS = (size_t)round_up8((int)(D + Dh));
+  L.ws_hi = take(Dh * KSh / 2 + 8);
+  L.ws_lo = take(Dh * KSh / 2 + 8);
   L.layer0 = o;
   size_t lo = 0;
   auto ltake = [&](size_t n) { size_t r = lo; lo += align_up(n * 4) / 4; return r; };
@@ -54,6 +57,10 @@ FoldLayout make_fold_layout(const qagnn_shape& s) {
   L.w1_lo = ltake(D * D / 2);
   L.w2_hi = ltake(D * D / 2);
   L.w2_lo = ltake(D * D / 2);
+  L.wps = ltake(3 * (size_t)s.H * DP * KS);
+  L.wps_hi = ltake(3 * (size_t)s.H * DP * KS / 2 + 8);
+  L.wps_lo = ltake(3 * (size_t)s.H * DP * KS / 2 + 8);
+  L.tbias = ltake((size_t)s.T * 3 * s.H * DP);
   L.layer_stride = lo;
   L.total = o + lo * (size_t)(s.k > 0 ? s.k : 0);
   return L;
@@ -162,6 +169,28 @@ __global__ void fold_pad_projection_kernel(int D, int H, int DP, const float* __
   }
 }
 
+// fast projection operands: wps[r, :] = [wph[r, 0:D] | wph[r, D+Dh:2D] | 0-pad]  and
+// tbias[t, r] = bph[r] + sum_j wph[r, D + j] * type_tab[t, j]     (the type-embedding half of node_feature_extra, :65-66,:86)
+__global__ void fold_type_bias_kernel(int rows, int D, int T, int KS, const float* __restrict__ wph, const float* __restrict__ bph,
+                                      const float* __restrict__ type_tab, float* __restrict__ wps, float* __restrict__ tbias) {
+  const int Dh = D / 2, K = 2 * D;
+  const int64_t n_w = (int64_t)rows * KS, n_b = (int64_t)T * rows;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_w + n_b; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_w) {
+      const int64_t r = i / KS;
+      const int c = (int)(i % KS);
+      wps[i] = c < D ? wph[r * K + c] : (c < D + Dh ? wph[r * K + D + Dh + (c - D)] : 0.f);
+    } else {
+      const int64_t j = i - n_w;
+      const int t = (int)(j / rows);
+      const int64_t r = j % rows;
+      float acc = 0.f;
+      for (int q = 0; q < Dh; ++q) acc = fmaf(wph[r * K + D + q], type_tab[(size_t)t * Dh + q], acc);
+      tbias[j] = bph[r] + acc;
+    }
+  }
+}
+
 // [C, D] -> head-major zero-padded [H, C, DP]
 __global__ void fold_head_major_kernel(int C, int D, int H, int DP, const float* __restrict__ ke,
                                        const float* __restrict__ me, float* __restrict__ keh,
@@ -250,6 +279,19 @@ extern "C" int32_t qagnn_fold_weights(const qagnn_shape* shape, const qagnn_edge
         mp->vx_w, mp->vx_b, mp->score_basis, f + L.type_tab, f + L.basis, f + L.ws, f + L.bs, f + L.vcat, f + L.vbias);
     QAGNN_CHECK_LAUNCH();
     if (D % 2 == 0) QAGNN_RETURN_IF(split_bf16(f + L.vcat, 2 * D, D, 2 * D, f + L.vcat_hi, f + L.vcat_lo, 2 * D, st));
+    if (D % 8 == 0 && Dh % 2 == 0) {  // operands of the fast projection / tensor-core emb_score (qagnn_mp_forward)
+      const int KSh = round_up8(Dh), KS = round_up8(D + Dh), DP = head_dim_padded(D / shape->H);
+      QAGNN_RETURN_IF(split_bf16(f + L.ws, Dh, Dh, Dh, f + L.ws_hi, f + L.ws_lo, KSh, st));
+      const int rows = 3 * shape->H * DP;
+      for (int l = 0; l < shape->k; ++l) {
+        float* lb = f + L.layer0 + (size_t)l * L.layer_stride;
+        const int64_t tot = (int64_t)rows * KS + (int64_t)shape->T * rows;
+        fold_type_bias_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, D, shape->T, KS, lb + L.wph, lb + L.bph,
+                                                                           f + L.type_tab, lb + L.wps, lb + L.tbias);
+        QAGNN_CHECK_LAUNCH();
+        QAGNN_RETURN_IF(split_bf16(lb + L.wps, KS, rows, KS, lb + L.wps_hi, lb + L.wps_lo, KS, st));
+      }
+    }
   }
   return QAGNN_OK;
 }

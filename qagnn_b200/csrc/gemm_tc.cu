@@ -43,6 +43,8 @@ struct alignas(64) TcParams {
   int umma_n, n_step, N, stages;
   long long M;
   const float* bias;
+  const int64_t* row_class;  // optional: bias row = clamp(row_class[r], 0, n_class-1) * class_stride
+  int class_stride, n_class;
   int act;
   float* c_f32;
   int ldc;
@@ -324,6 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int n_tile = (int)(tile % n_tiles);
       const int n0 = n_tile * p.n_step;
       const int row0 = (int)((tile / n_tiles) * BM * CTAS + rank * BM) + quad * 32;  // first row of this warp
+      const float* bias_row = p.bias;  // per-row bias table (node-type classes): this thread's row is row0 + lane
+      if (p.row_class != nullptr) {
+        const long long r = (long long)row0 + lane;
+        long long c = r < p.M ? p.row_class[r] : 0;
+        c = c < 0 ? 0 : (c >= p.n_class ? p.n_class - 1 : c);
+        bias_row = p.bias + (size_t)c * p.class_stride;
+      }
       mbar_wait(&acc_full[acc], (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quad * 32) << 16);
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tmem_ld32(taddr + (uint32_t)tcol, v);
         if (p.bias != nullptr) {  // bias is indexed by GEMM column (padded like the weight rows)
           if (n0 + tcol + 32 <= p.N) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + tcol);
+            const float4* b4 = reinterpret_cast<const float4*>(bias_row + n0 + tcol);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 b = __ldg(b4 + i);
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (n0 + tcol + i < p.N) v[i] += __ldg(p.bias + n0 + tcol + i);
+              if (n0 + tcol + i < p.N) v[i] += __ldg(bias_row + n0 + tcol + i);
           }
         }
 #pragma unroll
@@ -495,7 +504,9 @@ bool gemm_tc_available() {  // QAGNN_GEMM=ffma forces the exact-fp32 FFMA path (
 }
 
 bool gemm_tc_shape_ok(int K1, int K2, int lda1, int lda2, int ldw, int N) {
-  return K1 > 0 && K1 % 8 == 0 && (K2 == 0 || K2 % 8 == 0) && lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldw % 8 == 0 && N >= 8;
+  // TMA needs 16-byte row strides (ld % 8); K itself may be anything (the tensor map clips and zero-fills), but the second
+  // segment's weight columns start at K1, which the k-block arithmetic wants even
+  return K1 > 0 && K1 % 2 == 0 && K2 >= 0 && lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldw % 8 == 0 && N >= 8;
 }
 
 int32_t split_bf16(const float* a, int lda, long long M, int K, void* hi, void* lo, int ldp, cudaStream_t st) {
@@ -558,6 +569,9 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   if (!ok) return QAGNN_ERR_CUDA;
   if ((out.f32 && (out.ldc % 4 != 0)) || (out.hi && (out.ldp % 8 != 0))) return QAGNN_ERR_UNSUPPORTED;
   p.bias = bias;
+  p.row_class = bias != nullptr ? out.row_class : nullptr;
+  p.class_stride = out.class_stride;
+  p.n_class = out.n_class > 0 ? out.n_class : 1;
   p.act = (int)act;
   p.c_f32 = out.f32;
   p.ldc = out.ldc;
