@@ -360,6 +360,7 @@ def run_b200_arm(args):
     ms_e2e_nodes = timed_e2e(runner_nodes, args.steps) if world == 1 else None
     # kernel-level pass: the same K steps launched kernel by kernel with the library's CUDA-event stage timers on the
     # launching stream (events cannot be timed inside a replayed graph); feeds `roofline`, `stages`, `gpu_launches`
+    mod.use_cuda_graph = False
     eager = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False)
     eager.run()
     ms_eager, launches, prof = timed(eager.run, args.steps, profile=True)

@@ -211,6 +211,14 @@ int32_t qagnn_attention_pool(int32_t B, int32_t n, int32_t D, int32_t n_head, co
                              const uint8_t *mask, const float *wk, const float *bk, const float *wv, const float *bv,
                              float *pooled, float *attn, void *stream);
 
+/* The same pooling with the rest of QAGNN.forward's tail (modeling_qagnn.py:172-187) in the kernel: the pool mask is derived
+ * from adj_lengths [B] and node_type [B,n] ((i >= len) | (type == 3), node 0 kept if everything is masked) and the row of
+ * cat(graph_vecs, sent_vecs, Z) is written in place into concat [B, 2D+S] (Z = X[b,0,:], sent_vecs [B,S]).  The caller
+ * all-gathers `concat` (multi-GPU) and applies the answer MLP. */
+int32_t qagnn_decoder_tail(int32_t B, int32_t n, int32_t D, int32_t n_head, int32_t S, const float *X, const float *qs,
+                           const int64_t *node_type, const int64_t *adj_lengths, const float *sent_vecs, const float *wk,
+                           const float *bk, const float *wv, const float *bv, float *concat, float *attn, void *stream);
+
 /* The step before the path: QAGNN.forward's input assembly (modeling_qagnn.py:153-167), eval mode, one kernel:
  *   H_out[b,0,:] = ctx[b,:] (= GELU(svec2nvec(sent_vecs)), caller-computed [B,D]);  H_out[b,i,:] = table[concept_ids[b,i]-1], i >= 1,
  *   with `table` [n_concept, D] the concept embedding after cpt_transform + GELU (folded once by the caller; the table is

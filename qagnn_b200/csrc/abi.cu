@@ -204,9 +204,15 @@ int32_t check_shape_fwd(const qagnn_shape* s) {
 // (shape.n_per_graph > 0 and the tiles fit), else the general CSR kernels.  QAGNN_MP_PATH=csr forces
 // the general path (A/B measurements).
 bool use_headtile(const qagnn_shape& s) {
-  const char* e = getenv("QAGNN_MP_PATH");  // read at every call: tests cover both paths in one process
-  const bool forced = e && strcmp(e, "csr") == 0;
+  const char* e = getenv("QAGNN_MP_PATH");  // read at every call: tests cover every path in one process
+  const bool forced = e && (strcmp(e, "csr") == 0 || strcmp(e, "basic") == 0);
   return !forced && headtile_supported(s);
+}
+// Without per-graph tiles: the column-sliced kernels (edge tables in shared memory) when the head width allows, else the
+// basic CSR kernels; QAGNN_MP_PATH=basic forces the latter.
+bool use_slice(const qagnn_shape& s) {
+  const char* e = getenv("QAGNN_MP_PATH");
+  return !(e && strcmp(e, "basic") == 0) && slice_supported(s);
 }
 
 // one GATConvE layer; `final_act` = ACT_NONE for the bare layer, ACT_GELU when called from mp_helper
@@ -228,6 +234,9 @@ int32_t layer_forward(const qagnn_shape& s, const FoldLayout& L, const WorkLayou
     if (tiled) {
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
                                                       ws + W.score, ws + W.alpha2, aggr, alpha_out, nullptr, nullptr, st));
+    } else if (use_slice(s)) {
+      QAGNN_RETURN_IF(launch_message_passing_slice(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score, aggr,
+                                                   alpha_out, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
                                              ws + W.alpha, aggr, alpha_out, st));
@@ -294,6 +303,9 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
       QAGNN_RETURN_IF(launch_message_passing_headtile(s, (const int32_t*)prep, pl, qkm, lb + L.keh, lb + L.meh,
                                                       ws + W.score, ws + W.alpha2, aggr, alpha_out,
                                                       fused_split ? ws + W.ap_hi : nullptr, ws + W.ap_lo, st));
+    } else if (use_slice(s)) {
+      QAGNN_RETURN_IF(launch_message_passing_slice(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score, aggr,
+                                                   alpha_out, st));
     } else {
       QAGNN_RETURN_IF(launch_message_passing(s, (const int32_t*)prep, pl, qkm, lb + L.ke, lb + L.me, ws + W.score,
                                              ws + W.alpha, aggr, alpha_out, st));

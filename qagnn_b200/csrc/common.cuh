@@ -168,6 +168,12 @@ int32_t launch_message_passing(const qagnn_shape& s, const int32_t* prep_base, c
                                const float* qkm, const float* ke, const float* me, float* score, float* alpha,
                                float* aggr, float* alpha_out, cudaStream_t st);
 
+// column-sliced kernels with the edge tables in shared memory, for graphs too large for the per-graph tiles (mp_slice.cu)
+bool slice_supported(const qagnn_shape& s);
+int32_t launch_message_passing_slice(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
+                                     const float* qkm, const float* ke, const float* me, float* score, float* aggr,
+                                     float* alpha_out, cudaStream_t st);
+
 int32_t launch_message_passing_backward(const qagnn_shape& s, const int32_t* prep_base, const qagnn_prep_layout& pl,
                                         const int32_t* combo_order, const float* qkm, const float* ke, const float* me,
                                         const float* alpha_s, const float* d_aggr, float* ds, float* d_qkm, float* d_ke,

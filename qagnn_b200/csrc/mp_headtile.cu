@@ -31,6 +31,7 @@
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -198,7 +199,9 @@ __global__ void __launch_bounds__((WMAX + 1) * 32, 1) mp_headtile_kernel(const H
   auto tile_addr = [&](uint32_t base, uint32_t w) { return base + ((w & 0xffffu) << 4); };
   auto table_addr = [&](uint32_t base, uint32_t w) { return base + (w >> 15); };
 
-  auto grab = [&](uint32_t counter) {  // next work item of this phase (one shared-memory atomic per warp)
+  // next work item of this phase: one shared-memory atomic per warp.  (A static stride — warp w takes items w, w+W, ... —
+  // needs no atomic but measured 122 vs 115 us/layer at cfg2: the warps drift apart inside a tile, profiles/r2_mp_tuning.md)
+  auto grab = [&](uint32_t counter) {
     int v = 0;
     if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(counter) : "memory");
     return __shfl_sync(0xffffffffu, v, 0);
@@ -441,6 +444,8 @@ __global__ void __launch_bounds__((WMAX + 1) * 32, 1) mp_headtile_kernel(const H
         const uint32_t pko = e0.x;
         const float wv = __uint_as_float(e0.y);  // 0 beyond this node's degree
         const int lim = min(8, maxdeg - i0);
+        // (broadcasting all 8 {offsets word, a'} pairs up front, as phase 1 does with its offsets words, costs 16 registers
+        //  here and measured 123 vs 112 us/layer: reverted, profiles/r2_mp_tuning.md)
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           if (j + 1 < lim) {  // warp-uniform
@@ -565,8 +570,9 @@ HeadTilePlan make_plan(const qagnn_shape& s) {
   const long long G = s.N / s.n_per_graph, Gc = (G + pl.S - 1) / pl.S;
   if ((Gc * pl.nquads + 4 * kWarpsWide) * (long long)pl.nquads >= ((long long)1 << 32)) return pl;
   // two graphs' quads can be in flight at once; more warps than that would only spin
+  // (24 warps at 72 registers beat 31 at 64 with spills: 112 vs 115 us/layer at cfg2, profiles/r2_mp_tuning.md)
   int W = 2 * pl.nquads;
-  if (W > kWarpsWide) W = kWarpsWide;
+  if (W > kWarpsNarrow) W = kWarpsNarrow;
   const int fw = forced_warps();
   if (fw) W = fw;
   pl.W = W;

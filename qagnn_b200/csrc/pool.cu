@@ -15,14 +15,21 @@
 namespace qagnn {
 namespace {
 
-constexpr int kPoolThreads = 256;
+constexpr int kPoolThreads = 512;  // latency-bound kernel: 16 warps per graph keep enough row loads in flight
 
-// dynamic smem: qk[nh][D] | logit[nh][n] | xs[nh][D] | red[32]
+// dynamic smem: qk[nh][D] | logit[nh][n] | xs[nh][D] | cst[nh, padded to 8] | part[warps][nh][D]
 __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int D, int nh, const float* __restrict__ X,
                                                                         const float* __restrict__ qs, const unsigned char* __restrict__ mask,
                                                                         const float* __restrict__ wk, const float* __restrict__ bk,
                                                                         const float* __restrict__ wv, const float* __restrict__ bv,
-                                                                        float* __restrict__ pooled, float* __restrict__ attn_out, int B) {
+                                                                        float* __restrict__ pooled, float* __restrict__ attn_out, int B,
+                                                                        const int64_t* __restrict__ node_type = nullptr,
+                                                                        const int64_t* __restrict__ adj_lengths = nullptr,
+                                                                        const float* __restrict__ sent = nullptr, int S = 0,
+                                                                        int pooled_ld = 0) {
+  // mask == nullptr: "decoder tail" mode (modeling_qagnn.py:172-187) — the pool mask is derived here from adj_lengths and
+  // node_type, and the row of cat(graph_vecs, sent_vecs, Z) is written in place: pooled -> columns [0, D) of a
+  // [B, pooled_ld = 2D+S] buffer, sent_vecs -> [D, D+S), Z = X[b, 0, :] -> [D+S, 2D+S)
   extern __shared__ float sm[];
   float* qk = sm;                  // [nh][D]   W_k,hᵀ qs_h
   float* logit = qk + nh * D;      // [nh][n]
@@ -31,10 +38,22 @@ __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int
   const int b = blockIdx.x, tid = threadIdx.x, dk = D / nh;
   const float inv_temp = 1.0f / sqrtf((float)dk);
   const float* Xb = X + (size_t)b * n * D;
+  const bool tail = mask == nullptr;
+  if (!tail) pooled_ld = D;
+  int len = n;
+  bool all_masked = false;
+  if (tail) {
+    len = (int)min((int64_t)n, max((int64_t)0, adj_lengths[b]));
+    // mask = (i >= len) | (type == 3); a fully masked row keeps node 0 (:174-176)
+    int any_open = 0;
+    for (int i = tid; i < len; i += kPoolThreads) any_open |= node_type[(size_t)b * n + i] != 3;
+    all_masked = __syncthreads_or(any_open) == 0;
+  }
   // fold the key projection into the query: qk[h][j] = Σ_{r in head h} qs[b, r] * wk[r, j]
   for (int idx = tid; idx < nh * D; idx += kPoolThreads) {
     const int h = idx / D, j = idx % D;
     float acc = 0.f;
+#pragma unroll 10
     for (int r = 0; r < dk; ++r) acc = fmaf(qs[(size_t)b * D + h * dk + r], wk[(size_t)(h * dk + r) * D + j], acc);
     qk[idx] = acc;
   }
@@ -44,16 +63,52 @@ __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int
     cst[tid] = acc;
   }
   __syncthreads();
-  // logits: one warp per node, lanes over D
+  // logits: warps split the nodes, lanes the columns; 4 nodes per step so that up to 16 independent 128-byte row-segment
+  // loads are in flight per warp (the tile comes from HBM/L2 exactly here)
   const int warp = tid >> 5, lane = tid & 31, nwarps = kPoolThreads / 32;
-  for (int i = warp; i < n; i += nwarps) {
-    const bool masked = mask[(size_t)b * n + i] != 0;
-    for (int h = 0; h < nh; ++h) {
-      float acc = 0.f;
-      for (int j = lane; j < D; j += 32) acc = fmaf(qk[h * D + j], Xb[(size_t)i * D + j], acc);
+  for (int i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
+    float accl[4][8];  // [node][head], up to 8 heads
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) logit[h * n + i] = masked ? -INFINITY : (acc + cst[h]) * inv_temp;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) accl[r][h] = 0.f;
+    for (int j0 = 0; j0 < D; j0 += 32 * 4) {
+      float x[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = j0 + 32 * c + lane;
+          x[r][c] = (i0 + r < n && j < D) ? Xb[(size_t)(i0 + r) * D + j] : 0.f;
+        }
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < nh) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = j0 + 32 * c + lane;
+            const float qv = j < D ? qk[h * D + j] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) accl[r][h] = fmaf(qv, x[r][c], accl[r][h]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+      if (i >= n) break;
+      const bool masked = tail ? ((i >= len || node_type[(size_t)b * n + i] == 3) && !(all_masked && i == 0))
+                               : mask[(size_t)b * n + i] != 0;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < nh) {
+          float acc = accl[r][h];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == 0) logit[h * n + i] = masked ? -INFINITY : (acc + cst[h]) * inv_temp;
+        }
+      }
     }
   }
   __syncthreads();
@@ -78,21 +133,64 @@ __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int
     }
   }
   __syncthreads();
-  // attention-weighted node sum: xs[h][j] = Σ_i attn[h][i] * X[i][j]   (threads over j, all heads at once)
-  for (int j = tid; j < D; j += kPoolThreads) {
-    for (int h = 0; h < nh; ++h) {
-      float acc = 0.f;
-      for (int i = 0; i < n; ++i) acc = fmaf(logit[h * n + i], Xb[(size_t)i * D + j], acc);
-      xs[h * D + j] = acc;
+  // attention-weighted node sum: xs[h][j] = Σ_i attn[h][i] * X[i][j].  Warps split the nodes, lanes the columns (coalesced
+  // 128-byte row segments, every load independent of the accumulators: the kernel is latency bound, so what matters is
+  // how many loads are in flight); per-warp partial sums meet in shared memory.
+  float* part = cst + ((nh + 7) / 8) * 8;  // [nwarps][nh][D]
+  for (int j0 = 0; j0 < D; j0 += 32 * 4) {
+    float acc[4][4];  // [column chunk][head] — up to 4 heads per pass
+    for (int h0 = 0; h0 < nh; h0 += 4) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) acc[c][hh] = 0.f;
+#pragma unroll 4
+      for (int i = warp; i < n; i += nwarps) {
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = j0 + 32 * c + lane;
+          x[c] = j < D ? Xb[(size_t)i * D + j] : 0.f;
+        }
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          if (h0 + hh < nh) {
+            const float a = logit[(h0 + hh) * n + i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][hh] = fmaf(a, x[c], acc[c][hh]);
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = j0 + 32 * c + lane;
+          if (h0 + hh < nh && j < D) part[((size_t)warp * nh + h0 + hh) * D + j] = acc[c][hh];
+        }
     }
   }
   __syncthreads();
-  // value projection of the pooled vector: pooled[b, h*dv + r] = wv[h*dv + r, :]·xs[h] + bv
-  for (int idx = tid; idx < D; idx += kPoolThreads) {
+  for (int idx = tid; idx < nh * D; idx += kPoolThreads) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += part[(size_t)w * nh * D + idx];
+    xs[idx] = acc;
+  }
+  __syncthreads();
+  // value projection of the pooled vector: pooled[b, h*dv + r] = wv[h*dv + r, :]·xs[h] + bv   (one warp per output row:
+  // coalesced reads of the weight row, shuffle reduction)
+  for (int idx = warp; idx < D; idx += nwarps) {
     const int h = idx / dk;
-    float acc = bv[idx];
-    for (int j = 0; j < D; ++j) acc = fmaf(wv[(size_t)idx * D + j], xs[h * D + j], acc);
-    pooled[(size_t)b * D + idx] = acc;
+    float acc = 0.f;
+    for (int j = lane; j < D; j += 32) acc = fmaf(wv[(size_t)idx * D + j], xs[h * D + j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) pooled[(size_t)b * pooled_ld + idx] = acc + bv[idx];
+  }
+  if (tail) {
+    float* row = pooled + (size_t)b * pooled_ld;
+    for (int j = tid; j < S; j += kPoolThreads) row[D + j] = sent[(size_t)b * S + j];
+    for (int j = tid; j < D; j += kPoolThreads) row[D + S + j] = Xb[j];
   }
 }
 
@@ -166,12 +264,35 @@ extern "C" int32_t qagnn_decoder_head(int32_t B, int32_t n, int32_t D, const int
   return QAGNN_OK;
 }
 
+extern "C" int32_t qagnn_decoder_tail(int32_t B, int32_t n, int32_t D, int32_t n_head, int32_t S, const float* X, const float* qs,
+                                      const int64_t* node_type, const int64_t* adj_lengths, const float* sent_vecs,
+                                      const float* wk, const float* bk, const float* wv, const float* bv, float* concat,
+                                      float* attn, void* stream) {
+  if (B <= 0 || n <= 0 || D <= 0 || n_head <= 0 || D % n_head != 0 || S < 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (n_head > 8) return QAGNN_ERR_UNSUPPORTED;
+  if (!X || !qs || !node_type || !adj_lengths || !sent_vecs || !wk || !bk || !wv || !bv || !concat || !attn)
+    return QAGNN_ERR_INVALID_ARGUMENT;
+  const size_t smem = ((size_t)2 * n_head * D + (size_t)n_head * n + n_head + 16 + (size_t)(kPoolThreads / 32) * n_head * D) * sizeof(float);
+  if (smem > 200 * 1024) return QAGNN_ERR_UNSUPPORTED;
+  static size_t attr[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr[dev]) {
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(attention_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[dev] = smem;
+  }
+  attention_pool_kernel<<<B, kPoolThreads, smem, (cudaStream_t)stream>>>(n, D, n_head, X, qs, nullptr, wk, bk, wv, bv, concat, attn, B,
+                                                                         node_type, adj_lengths, sent_vecs, S, 2 * D + S);
+  QAGNN_CHECK_LAUNCH();
+  return QAGNN_OK;
+}
+
 extern "C" int32_t qagnn_attention_pool(int32_t B, int32_t n, int32_t D, int32_t n_head, const float* X, const float* qs,
                                         const uint8_t* mask, const float* wk, const float* bk, const float* wv, const float* bv,
                                         float* pooled, float* attn, void* stream) {
   if (B <= 0 || n <= 0 || D <= 0 || n_head <= 0 || D % n_head != 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (n_head > 8) return QAGNN_ERR_UNSUPPORTED;
   if (!X || !qs || !mask || !wk || !bk || !wv || !bv || !pooled || !attn) return QAGNN_ERR_INVALID_ARGUMENT;
-  const size_t smem = ((size_t)2 * n_head * D + (size_t)n_head * n + n_head + 8) * sizeof(float);
+  const size_t smem = ((size_t)2 * n_head * D + (size_t)n_head * n + n_head + 16 + (size_t)(kPoolThreads / 32) * n_head * D) * sizeof(float);
   if (smem > 200 * 1024) return QAGNN_ERR_UNSUPPORTED;
   static size_t attr[kMaxDevices] = {0};
   const int dev = current_device();

@@ -76,6 +76,34 @@ class MultiheadAttPoolLayer(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self._fused_ok = True
 
+    def pool_concat(self, q, k, node_type, adj_lengths):
+        """Eval-mode decoder tail in ONE kernel (qagnn_decoder_tail): derives the pool mask from adj_lengths / node_type,
+        pools, and returns (cat(pooled, q, k[:, 0]) [b, 2*d_k_original + d_q_original], attn) — modeling_qagnn.py:172-187.
+        Returns None when the fused kernel cannot take the shape (caller falls back to mask + forward + cat)."""
+        if (self.training or not k.is_cuda or k.dtype != torch.float32 or not self._fused_ok
+                or (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad))):
+            return None
+        from . import _lib
+        lib = _lib.load()
+        b, l, D = k.shape
+        S = q.size(1)
+        qc = _lib.f32c(q, "q")
+        qs = self.w_qs(qc).detach().contiguous()
+        kc = _lib.f32c(k, "k")
+        concat = torch.empty(b, 2 * D + S, dtype=torch.float32, device=k.device)
+        attn = torch.empty(self.n_head * b, l, dtype=torch.float32, device=k.device)
+        with torch.cuda.device(k.device):
+            st = lib.qagnn_decoder_tail(b, l, D, self.n_head, S, _lib.ptr(kc), _lib.ptr(qs), _lib.ptr(_lib.i64c(node_type, "node_type")),
+                                        _lib.ptr(_lib.i64c(adj_lengths, "adj_lengths")), _lib.ptr(qc),
+                                        _lib.ptr(self.w_ks.weight.detach()), _lib.ptr(self.w_ks.bias.detach()),
+                                        _lib.ptr(self.w_vs.weight.detach()), _lib.ptr(self.w_vs.bias.detach()),
+                                        _lib.ptr(concat), _lib.ptr(attn), _lib.stream_ptr(k.device))
+        if st == -5:
+            self._fused_ok = False
+            return None
+        _lib.check(st, "qagnn_decoder_tail")
+        return concat, attn
+
     def forward(self, q, k, mask=None):
         b, l, _ = k.shape
         nh, dk, dv = self.n_head, self.d_k, self.d_v

@@ -522,6 +522,11 @@ class QAGNN(nn.Module):
             s = (s / (mean_norm.unsqueeze(1) + 1e-05)).unsqueeze(2)
 
         gnn_output = self.gnn(gnn_input, adj, node_type_ids, s)
+        fused = self.pooler.pool_concat(sent_vecs, gnn_output, node_type_ids, adj_lengths) if not self.training else None
+        if fused is not None:  # pool mask + pooling + cat(graph_vecs, sent_vecs, Z) in one kernel (dropout_fc = identity in eval)
+            if cache_output:
+                self.concept_ids, self.adj, self.pool_attn = concept_ids, adj, fused[1]
+            return fused
         Z_vecs = gnn_output[:, 0]
         mask = (pos >= adj_lengths.unsqueeze(1)) | (node_type_ids == 3)
         mask[:, 0] = mask[:, 0] & ~mask.all(1)  # a fully masked row keeps node 0 (:176; written without a host sync)

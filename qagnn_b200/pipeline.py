@@ -45,12 +45,16 @@ class DecoderStep:
     def _eager(self):
         d = self.inp
         out = self.gnn(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
-        n = out.size(1)
-        pos = torch.arange(n, device=out.device)
-        mask = (pos >= d["adj_lengths"].unsqueeze(1)) | (d["node_type"] == 3)            # modeling_qagnn.py:174-175
-        mask[:, 0] = mask[:, 0] & ~mask.all(1)                                              # :176
-        graph_vecs, pool_attn = self.pooler(d["sent_vecs"], out, mask)                      # :180
-        concat = torch.cat((graph_vecs, d["sent_vecs"], out[:, 0]), 1)                      # :187 (dropout = identity in eval)
+        fused = self.pooler.pool_concat(d["sent_vecs"], out, d["node_type"], d["adj_lengths"])  # :172-187 in one kernel
+        if fused is not None:
+            concat, pool_attn = fused
+        else:
+            n = out.size(1)
+            pos = torch.arange(n, device=out.device)
+            mask = (pos >= d["adj_lengths"].unsqueeze(1)) | (d["node_type"] == 3)        # modeling_qagnn.py:174-175
+            mask[:, 0] = mask[:, 0] & ~mask.all(1)                                          # :176
+            graph_vecs, pool_attn = self.pooler(d["sent_vecs"], out, mask)                  # :180
+            concat = torch.cat((graph_vecs, d["sent_vecs"], out[:, 0]), 1)                  # :187 (dropout = identity in eval)
         full = _dist.all_gather_rows(concat, self.world, self.group, True, self.full)       # the path's one collective
         return self.fc(full), pool_attn, out                                                # :188
 

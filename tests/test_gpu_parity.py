@@ -266,7 +266,7 @@ def test_bench_workload_matches_oracle_on_first_middle_and_last_graphs():
 
 
 # ---- every launch-time switch the shipped library keeps (read at each call) has GPU coverage ------------------------
-@pytest.mark.parametrize("env", [{"QAGNN_MP_PATH": "csr"}, {"QAGNN_TC_2CTA": "0"}, {"QAGNN_GEMM": "ffma"},
+@pytest.mark.parametrize("env", [{"QAGNN_MP_PATH": "csr"}, {"QAGNN_MP_PATH": "basic"}, {"QAGNN_TC_2CTA": "0"}, {"QAGNN_GEMM": "ffma"},
                                  {"QAGNN_MP_WARPS": "24"}, {"QAGNN_MP_WARPS": "31"}, {"QAGNN_MP_WARPS": "7"},
                                  {"QAGNN_MP_FASTPROJ": "0"}])
 @pytest.mark.parametrize("name", ["cfg2small_peaky", "cfg2small_realistic", "tiny_realistic_d100", "no_edges"])
@@ -304,6 +304,35 @@ def test_large_graph_general_path_matches_oracle():
     assert torch.equal(ei_g.cpu(), ei2)
     Hh.assert_close(alpha, ref_alpha, "alpha")
     Hh.assert_close(out, ref_out, "out")
+
+
+@pytest.mark.parametrize("path", ["auto", "basic"])
+def test_stress_shape_full_size_graph_matches_oracle(path, monkeypatch):
+    """BASELINE.json configs[4] at FULL per-graph size (2000 nodes / 20000 edges, hidden 1024, 8 heads): one GATConvE layer on
+    one such graph against the CPU oracle, through the column-sliced kernels (auto) and the basic CSR kernels."""
+    if path == "basic":
+        monkeypatch.setenv("QAGNN_MP_PATH", "basic")
+    n, e, D, Hh_ = 2000, 20000, 1024, 8
+    inp = O.synth_graph_batch(1, n, e, D, 38, seed=55)
+    sd = O.random_state_dict(1, D, 4, 38, "peaky", seed=55)
+    x = inp["H"].view(-1, D).contiguous()
+    extra = torch.randn(x.shape, generator=torch.Generator().manual_seed(6)) * 0.5
+    nt = inp["node_type"].view(-1)
+    torch.set_num_threads(min(32, torch.get_num_threads() if torch.get_num_threads() > 0 else 8))
+    ref_out, ei2, ref_alpha, ref_aggr = O.gatconve_forward(sd, "gnn_layers.0", x, inp["edge_index"], inp["edge_type"], nt, extra,
+                                                           4, 38, head_count=Hh_)
+    enc = torch.nn.Sequential(torch.nn.Linear(38 + 1 + 8, D), torch.nn.BatchNorm1d(D), torch.nn.ReLU(), torch.nn.Linear(D, D))
+    layer = qagnn_b200.GATConvE(None, D, 4, 38, enc, head_count=Hh_).eval()
+    layer.load_state_dict({k_[len("gnn_layers.0."):]: v for k_, v in sd.items() if k_.startswith("gnn_layers.0.")})
+    layer = layer.to(DEV)
+    (out, (ei_g, alpha)), aggr = layer(x.to(DEV), inp["edge_index"].to(DEV), inp["edge_type"].to(DEV), nt.to(DEV), extra.to(DEV),
+                                       return_attention_weights=True, return_aggr=True)
+    assert torch.equal(ei_g.cpu(), ei2)
+    Hh.assert_close(alpha, ref_alpha, f"alpha ({path})")
+    Hh.assert_close(aggr, ref_aggr, f"aggr ({path})")
+    Hh.assert_close(out, ref_out, f"out ({path})")
+    again = layer(x.to(DEV), inp["edge_index"].to(DEV), inp["edge_type"].to(DEV), nt.to(DEV), extra.to(DEV))
+    assert torch.equal(again, out), "the large-graph path must be run-to-run bit-identical"
 
 
 def test_lm_qagnn_forward_api_with_packed_and_nested_adjacency():
@@ -460,6 +489,9 @@ def test_decoder_step_graph_matches_module_composition():
     assert step.graph is not None
     for seed in (11, 12):
         nd, ninp = batch(seed)
+        if seed != 11:  # same adjacency buffers (their length is part of the captured graph), new features / scores / sentences
+            for k_ in ("edge_index", "edge_type", "node_type", "adj_lengths"):
+                nd[k_], ninp[k_] = d[k_].clone(), inp[k_]
         for k_ in DecoderStep.FIELDS:
             d[k_].copy_(nd[k_])
         logits, attn, gout = (t.clone() for t in step.run())

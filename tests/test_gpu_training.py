@@ -19,9 +19,11 @@ def _module(fx, sd, dropout=0.0):
     return mod.to(DEV)
 
 
-def _grad_close(got, ref, what):
-    # gradients span orders of magnitude across parameters: 1e-4 relative to the tensor's own scale, plus 1e-4 relative
-    scale = max(float(ref.abs().max()), 1e-6)
+def _grad_close(got, ref, what, floor=0.0):
+    # gradients span orders of magnitude across parameters: 1e-4 relative to the tensor's own scale, plus 1e-4 relative.
+    # `floor`: a gradient that is mathematically zero (the bias in front of a BatchNorm) is pure rounding noise in both
+    # implementations; it is compared on the scale of the largest gradient of the model instead of its own
+    scale = max(float(ref.abs().max()), floor, 1e-6)
     Hh.assert_close(got, ref, what, atol=1e-4 * scale, rtol=1e-4)
 
 
@@ -42,9 +44,10 @@ def test_training_forward_and_gradients_match_reference(name):
     _grad_close(score.grad, fx["grad_score"], "dL/dscore")
     got = dict(mod.named_parameters())
     assert sorted(got) == sorted(fx["grads"]), "parameter names (shared edge_encoder de-duplicated) differ from the reference"
+    gmax = max(float(g.abs().max()) for g in fx["grads"].values() if g is not None)
     for pname, ref_g in fx["grads"].items():
         assert got[pname].grad is not None, pname
-        _grad_close(got[pname].grad, ref_g, f"dL/d{pname}")
+        _grad_close(got[pname].grad, ref_g, f"dL/d{pname}", floor=1e-2 * gmax)
     bufs = dict(mod.named_buffers())
     for bname, ref_b in fx["buffers_after"].items():
         if "num_batches" in bname:
