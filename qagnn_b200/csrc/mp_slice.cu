@@ -21,7 +21,7 @@ namespace qagnn {
 namespace {
 
 constexpr int kSliceThreads = 1024;
-constexpr int kUnroll = 4;  // edges in flight per lane group
+constexpr int kUnroll = 2;  // edges in flight per lane group (x 2 chunks per lane at SL = 64)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -34,6 +34,17 @@ __device__ __forceinline__ void load_table_slice(float* tab, const float* __rest
   }
 }
 
+// lanes per edge: 8 lanes x 2 float4 for SL = 64 (half the shuffles, index loads and address arithmetic per gathered byte of
+// a 16-lane x 1-chunk mapping: the kernels are instruction bound, profiles/r2_cfg5_ncu.md), else one float4 per lane
+template <int SL> struct SliceMap {
+  static constexpr int CPL = SL >= 64 ? 2 : 1;   // float4 chunks per lane
+  static constexpr int LPE = SL / (4 * CPL);     // lanes per edge
+  static constexpr int EPW = 32 / LPE;           // edges a warp handles side by side
+};
+
+// A warp walks TWO consecutive nodes per step: their CSR ranges are adjacent, so the pair is one run of ~2*degree edges
+// (at degree 11 and 8 edge slots per iteration a single node wastes 31 % of the slots, a pair 8 %), and the index words
+// of the next iteration are requested before the current rows are consumed (one L2 round trip hidden per iteration).
 template <int SL>
 __global__ void __launch_bounds__(kSliceThreads, 1) mp_slice_scores_kernel(int64_t N, int D, int H, int C, int parts,
                                                                            const int32_t* __restrict__ rowptr_src,
@@ -43,36 +54,64 @@ __global__ void __launch_bounds__(kSliceThreads, 1) mp_slice_scores_kernel(int64
                                                                            const float* __restrict__ ke, float* __restrict__ score,
                                                                            int slices_per_head) {
   extern __shared__ __align__(16) float tab[];  // [C][SL]
-  constexpr int LPE = SL / 4;                   // lanes per edge (one float4 each)
-  constexpr int EPW = 32 / LPE;                 // edges a warp handles side by side
+  constexpr int CPL = SliceMap<SL>::CPL, LPE = SliceMap<SL>::LPE, EPW = SliceMap<SL>::EPW, RCH = SL / 4;
   const int slice = blockIdx.x % (D / SL), part = blockIdx.x / (D / SL);
   const int col0 = slice * SL, h = col0 / (D / H);
   load_table_slice<SL>(tab, ke, C, D, col0);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / LPE, lc = lane % LPE;
-  const int ld = 3 * D;
+  const uint32_t ld = 3u * (uint32_t)D;
+  const float4* tab4 = reinterpret_cast<const float4*>(tab);
+  const float* kbase = qkm + D + col0 + 4 * lc;  // Kx slice, this lane's first chunk (chunk k is LPE float4 further)
   const int64_t u0 = N * part / parts, u1 = N * (part + 1) / parts;
-  for (int64_t u = u0 + warp; u < u1; u += nwarps) {
-    const float4 q = ldg4(qkm + u * ld + col0 + 4 * lc);
-    const int beg = rowptr_src[u], end = rowptr_src[u + 1];
+  for (int64_t u = u0 + 2 * warp; u < u1; u += 2 * nwarps) {
+    const bool two = u + 1 < u1;
+    float4 qa[CPL], qb[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      qa[k] = ldg4(qkm + u * ld + col0 + 4 * (lc + LPE * k));
+      qb[k] = two ? ldg4(qkm + (u + 1) * ld + col0 + 4 * (lc + LPE * k)) : qa[k];
+    }
+    const int beg = rowptr_src[u], mid = rowptr_src[u + 1], end = two ? rowptr_src[u + 2] : mid;
+    // index words of the first iteration
+    uint32_t tn[kUnroll];
+    int cn[kUnroll];
+#pragma unroll
+    for (int r = 0; r < kUnroll; ++r) {
+      const int p = beg + sub + r * EPW;
+      tn[r] = p < end ? (uint32_t)csr_src_tgt[p] : 0u;
+      cn[r] = p < end ? csr_src_combo[p] : 0;
+    }
     for (int pb = beg; pb < end; pb += EPW * kUnroll) {  // warp-uniform trip count: the shuffles below need all lanes
       const int p0 = pb + sub;
-      float4 kx[kUnroll];
+      float4 kx[kUnroll][CPL];
       int cb[kUnroll];
 #pragma unroll
       for (int r = 0; r < kUnroll; ++r) {
-        const int p = p0 + r * EPW;
-        const bool ok = p < end;
-        const int t = ok ? csr_src_tgt[p] : 0;
-        cb[r] = ok ? csr_src_combo[p] : 0;
-        kx[r] = ok ? ldg4(qkm + (int64_t)t * ld + D + col0 + 4 * lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = p0 + r * EPW < end;
+        cb[r] = cn[r];
+        const float* row = kbase + (size_t)(tn[r] * ld);  // N * 3D < 2^31 (checked by the plan)
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) kx[r][k] = ok ? ldg4(row + 4 * LPE * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int r = 0; r < kUnroll; ++r) {  // next iteration's index words, in flight while this one's rows arrive
+        const int p = p0 + EPW * kUnroll + r * EPW;
+        tn[r] = p < end ? (uint32_t)csr_src_tgt[p] : 0u;
+        cn[r] = p < end ? csr_src_combo[p] : 0;
       }
 #pragma unroll
       for (int r = 0; r < kUnroll; ++r) {
         const int p = p0 + r * EPW;
-        const float4 kt = reinterpret_cast<const float4*>(tab)[cb[r] * LPE + lc];
-        float s = (q.x * (kx[r].x + kt.x) + q.y * (kx[r].y + kt.y)) + (q.z * (kx[r].z + kt.z) + q.w * (kx[r].w + kt.w));
+        const bool first = p < mid;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float4 kt = tab4[cb[r] * RCH + lc + LPE * k];
+          const float4 q = first ? qa[k] : qb[k];
+          s += (q.x * (kx[r][k].x + kt.x) + q.y * (kx[r][k].y + kt.y)) + (q.z * (kx[r][k].z + kt.z) + q.w * (kx[r][k].w + kt.w));
+        }
 #pragma unroll
         for (int o = LPE / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lc == 0 && p < end) {
@@ -123,51 +162,87 @@ __global__ void __launch_bounds__(kSliceThreads, 1) mp_slice_aggregate_kernel(in
                                                                               const float* __restrict__ alpha,
                                                                               float* __restrict__ aggr) {
   extern __shared__ __align__(16) float tab[];  // [C][SL]
-  constexpr int LPE = SL / 4, EPW = 32 / LPE;
+  constexpr int CPL = SliceMap<SL>::CPL, LPE = SliceMap<SL>::LPE, EPW = SliceMap<SL>::EPW, RCH = SL / 4;
   const int slice = blockIdx.x % (D / SL), part = blockIdx.x / (D / SL);
   const int col0 = slice * SL, h = col0 / (D / H);
   load_table_slice<SL>(tab, me, C, D, col0);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / LPE, lc = lane % LPE;
-  const int ld = 3 * D;
+  const uint32_t ld = 3u * (uint32_t)D;
+  const float4* tab4 = reinterpret_cast<const float4*>(tab);
+  const float* mbase = qkm + 2 * D + col0 + 4 * lc;
+  const float* abase = alpha + h;
   const int64_t v0 = N * part / parts, v1 = N * (part + 1) / parts;
-  for (int64_t v = v0 + warp; v < v1; v += nwarps) {
-    const int beg = rowptr_tgt[v], end = rowptr_tgt[v + 1];
-    // lane group `sub` sums edges beg+sub, beg+sub+EPW, ... in that order; the groups are combined in a fixed tree below,
-    // so the result is run-to-run identical
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t v = v0 + 2 * warp; v < v1; v += 2 * nwarps) {  // two consecutive targets per step (see the scores kernel)
+    const bool two = v + 1 < v1;
+    const int beg = rowptr_tgt[v], mid = rowptr_tgt[v + 1], end = two ? rowptr_tgt[v + 2] : mid;
+    // lane group `sub` sums edges beg+sub, beg+sub+EPW, ... of the pair's run in that order, each edge into its own target's
+    // accumulator; the groups are combined in a fixed tree below, so the result is run-to-run identical
+    float4 acca[CPL], accb[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acca[k] = accb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t sn[kUnroll], an[kUnroll];
+    int cn[kUnroll];
+#pragma unroll
+    for (int r = 0; r < kUnroll; ++r) {
+      const int p = beg + sub + r * EPW;
+      sn[r] = p < end ? (uint32_t)csr_tgt_src[p] : 0u;
+      cn[r] = p < end ? csr_tgt_combo[p] : 0;
+      an[r] = p < end ? (uint32_t)csr_tgt_apos[p] : 0u;
+    }
     for (int pb = beg; pb < end; pb += EPW * kUnroll) {
       const int p0 = pb + sub;
-      float4 mx[kUnroll];
+      float4 mx[kUnroll][CPL];
       int cb[kUnroll];
       float w[kUnroll];
 #pragma unroll
       for (int r = 0; r < kUnroll; ++r) {
-        const int p = p0 + r * EPW;
-        const bool ok = p < end;
-        const int s = ok ? csr_tgt_src[p] : 0;
-        cb[r] = ok ? csr_tgt_combo[p] : 0;
-        w[r] = ok ? alpha[(int64_t)csr_tgt_apos[p] * H + h] : 0.f;
-        mx[r] = ok ? ldg4(qkm + (int64_t)s * ld + 2 * D + col0 + 4 * lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = p0 + r * EPW < end;
+        cb[r] = cn[r];
+        w[r] = ok ? abase[(size_t)(an[r] * (uint32_t)H)] : 0.f;
+        const float* row = mbase + (size_t)(sn[r] * ld);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) mx[r][k] = ok ? ldg4(row + 4 * LPE * k) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int r = 0; r < kUnroll; ++r) {
-        const float4 mt = reinterpret_cast<const float4*>(tab)[cb[r] * LPE + lc];
-        acc.x += (mx[r].x + mt.x) * w[r];
-        acc.y += (mx[r].y + mt.y) * w[r];
-        acc.z += (mx[r].z + mt.z) * w[r];
-        acc.w += (mx[r].w + mt.w) * w[r];
+        const int p = p0 + EPW * kUnroll + r * EPW;
+        sn[r] = p < end ? (uint32_t)csr_tgt_src[p] : 0u;
+        cn[r] = p < end ? csr_tgt_combo[p] : 0;
+        an[r] = p < end ? (uint32_t)csr_tgt_apos[p] : 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < kUnroll; ++r) {
+        const bool first = p0 + r * EPW < mid;
+        const float wa = first ? w[r] : 0.f, wb = first ? 0.f : w[r];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float4 mt = tab4[cb[r] * RCH + lc + LPE * k];
+          const float mxv = mx[r][k].x + mt.x, myv = mx[r][k].y + mt.y, mzv = mx[r][k].z + mt.z, mwv = mx[r][k].w + mt.w;
+          acca[k].x += mxv * wa; acca[k].y += myv * wa; acca[k].z += mzv * wa; acca[k].w += mwv * wa;
+          accb[k].x += mxv * wb; accb[k].y += myv * wb; accb[k].z += mzv * wb; accb[k].w += mwv * wb;
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o >= LPE; o >>= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    for (int k = 0; k < CPL; ++k) {
+#pragma unroll
+      for (int o = 16; o >= LPE; o >>= 1) {
+        acca[k].x += __shfl_xor_sync(0xffffffffu, acca[k].x, o);
+        acca[k].y += __shfl_xor_sync(0xffffffffu, acca[k].y, o);
+        acca[k].z += __shfl_xor_sync(0xffffffffu, acca[k].z, o);
+        acca[k].w += __shfl_xor_sync(0xffffffffu, acca[k].w, o);
+        accb[k].x += __shfl_xor_sync(0xffffffffu, accb[k].x, o);
+        accb[k].y += __shfl_xor_sync(0xffffffffu, accb[k].y, o);
+        accb[k].z += __shfl_xor_sync(0xffffffffu, accb[k].z, o);
+        accb[k].w += __shfl_xor_sync(0xffffffffu, accb[k].w, o);
+      }
+      if (sub == 0) {
+        *reinterpret_cast<float4*>(aggr + v * D + col0 + 4 * (lc + LPE * k)) = acca[k];
+        if (two) *reinterpret_cast<float4*>(aggr + (v + 1) * D + col0 + 4 * (lc + LPE * k)) = accb[k];
+      }
     }
-    if (sub == 0) *reinterpret_cast<float4*>(aggr + v * D + col0 + 4 * lc) = acc;
   }
 }
 
@@ -184,7 +259,8 @@ SlicePlan make_slice_plan(const qagnn_shape& s) {
   const int d = s.D / s.H;
   int SL = d >= 64 ? 64 : d;
   if (SL != 16 && SL != 32 && SL != 64) return pl;
-  if (d % SL != 0 || d / SL > 2) return pl;  // at most two addends per logit: the atomic accumulation stays deterministic
+  if (d % SL != 0 || d / SL > 2) return pl;
+  if ((long long)s.N * 3 * s.D >= ((long long)1 << 31) || (long long)(s.N + s.E) * s.H >= ((long long)1 << 31)) return pl;  // 32-bit element offsets  // at most two addends per logit: the atomic accumulation stays deterministic
   const int C = s.R * s.T * s.T + s.T;
   static int sms_c[kMaxDevices] = {0}, smem_c[kMaxDevices] = {0};
   const int dev = current_device();

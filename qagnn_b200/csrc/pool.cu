@@ -15,10 +15,10 @@
 namespace qagnn {
 namespace {
 
-constexpr int kPoolThreads = 512;  // latency-bound kernel: 16 warps per graph keep enough row loads in flight
+constexpr int kPoolThreads = 256;  // latency-bound kernel: <= 64 registers so that 4 CTAs (graphs) share an SM
 
 // dynamic smem: qk[nh][D] | logit[nh][n] | xs[nh][D] | cst[nh, padded to 8] | part[warps][nh][D]
-__global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int D, int nh, const float* __restrict__ X,
+__global__ void __launch_bounds__(kPoolThreads, 4) attention_pool_kernel(int n, int D, int nh, const float* __restrict__ X,
                                                                         const float* __restrict__ qs, const unsigned char* __restrict__ mask,
                                                                         const float* __restrict__ wk, const float* __restrict__ bk,
                                                                         const float* __restrict__ wv, const float* __restrict__ bv,
@@ -57,56 +57,61 @@ __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int
     for (int r = 0; r < dk; ++r) acc = fmaf(qs[(size_t)b * D + h * dk + r], wk[(size_t)(h * dk + r) * D + j], acc);
     qk[idx] = acc;
   }
-  if (tid < nh) {
+  for (int h = tid >> 5; h < nh; h += kPoolThreads / 32) {  // one warp per head: qs_h . b_k,h
     float acc = 0.f;
-    for (int r = 0; r < dk; ++r) acc = fmaf(qs[(size_t)b * D + tid * dk + r], bk[tid * dk + r], acc);
-    cst[tid] = acc;
+    for (int r = tid & 31; r < dk; r += 32) acc = fmaf(qs[(size_t)b * D + h * dk + r], bk[h * dk + r], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) cst[h] = acc;
   }
   __syncthreads();
   // logits: warps split the nodes, lanes the columns; 4 nodes per step so that up to 16 independent 128-byte row-segment
   // loads are in flight per warp (the tile comes from HBM/L2 exactly here)
   const int warp = tid >> 5, lane = tid & 31, nwarps = kPoolThreads / 32;
   for (int i0 = warp * 4; i0 < n; i0 += nwarps * 4) {
-    float accl[4][8];  // [node][head], up to 8 heads
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) accl[r][h] = 0.f;
-    for (int j0 = 0; j0 < D; j0 += 32 * 4) {
-      float x[4][4];
+    for (int h0 = 0; h0 < nh; h0 += 4) {  // up to 4 heads per pass (register budget)
+      float accl[4][4];  // [node][head]
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j = j0 + 32 * c + lane;
-          x[r][c] = (i0 + r < n && j < D) ? Xb[(size_t)(i0 + r) * D + j] : 0.f;
-        }
+        for (int hh = 0; hh < 4; ++hh) accl[r][hh] = 0.f;
+      for (int j0 = 0; j0 < D; j0 += 32 * 4) {
+        float x[4][4];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        if (h < nh) {
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int j = j0 + 32 * c + lane;
-            const float qv = j < D ? qk[h * D + j] : 0.f;
+            x[r][c] = (i0 + r < n && j < D) ? Xb[(size_t)(i0 + r) * D + j] : 0.f;
+          }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) accl[r][h] = fmaf(qv, x[r][c], accl[r][h]);
+        for (int hh = 0; hh < 4; ++hh) {
+          if (h0 + hh < nh) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int j = j0 + 32 * c + lane;
+              const float qv = j < D ? qk[(h0 + hh) * D + j] : 0.f;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) accl[r][hh] = fmaf(qv, x[r][c], accl[r][hh]);
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = i0 + r;
-      if (i >= n) break;
-      const bool masked = tail ? ((i >= len || node_type[(size_t)b * n + i] == 3) && !(all_masked && i == 0))
-                               : mask[(size_t)b * n + i] != 0;
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + r;
+        if (i < n) {
+          const bool masked = tail ? ((i >= len || node_type[(size_t)b * n + i] == 3) && !(all_masked && i == 0))
+                                   : mask[(size_t)b * n + i] != 0;
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        if (h < nh) {
-          float acc = accl[r][h];
+          for (int hh = 0; hh < 4; ++hh) {
+            if (h0 + hh < nh) {
+              float acc = accl[r][hh];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          if (lane == 0) logit[h * n + i] = masked ? -INFINITY : (acc + cst[h]) * inv_temp;
+              for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+              if (lane == 0) logit[(h0 + hh) * n + i] = masked ? -INFINITY : (acc + cst[h0 + hh]) * inv_temp;
+            }
+          }
         }
       }
     }
@@ -179,13 +184,22 @@ __global__ void __launch_bounds__(kPoolThreads) attention_pool_kernel(int n, int
   __syncthreads();
   // value projection of the pooled vector: pooled[b, h*dv + r] = wv[h*dv + r, :]·xs[h] + bv   (one warp per output row:
   // coalesced reads of the weight row, shuffle reduction)
-  for (int idx = warp; idx < D; idx += nwarps) {
-    const int h = idx / dk;
-    float acc = 0.f;
-    for (int j = lane; j < D; j += 32) acc = fmaf(wv[(size_t)idx * D + j], xs[h * D + j], acc);
+  for (int r0 = warp * 4; r0 < D; r0 += nwarps * 4) {  // 4 rows per step: their weight loads are all independent
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < D; j += 32) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) pooled[(size_t)b * pooled_ld + idx] = acc + bv[idx];
+      for (int r = 0; r < 4; ++r) {
+        const int idx = min(r0 + r, D - 1);
+        acc[r] = fmaf(wv[(size_t)idx * D + j], xs[(idx / dk) * D + j], acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float a = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && r0 + r < D) pooled[(size_t)b * pooled_ld + r0 + r] = a + bv[r0 + r];
+    }
   }
   if (tail) {
     float* row = pooled + (size_t)b * pooled_ld;
