@@ -55,46 +55,52 @@ def b_alg_per_layer(N, E, D):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm (oracle/qagnn_oracle.py), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_graphs, seed=0, budget_s=None):
-    """Times the CPU restatement on `sample_graphs` graphs of the workload.  With `budget_s` the sample is shrunk
-    (never below 4 graphs) so that warmup+steps forwards fit the budget; steps and warmup are always honoured."""
+CPU_THREADS = 32  # pinned intra-op pool of the CPU arm (torch's pool degrades when oversubscribed on many-core hosts;
+#                   16-32 threads were the fastest sizes of every probe on the 128-cpu GPU boxes, round 1 and 2)
+
+
+def cpu_reference_run(steps, warmup, sample_graphs, seed=0, budget_s=None, full_batch_once=False):
+    """Times the CPU restatement on `sample_graphs` graphs of the workload with a PINNED thread-pool size.  With `budget_s`
+    the sample is shrunk (never below 4 graphs) so that warmup+steps forwards fit the budget; steps and warmup are always
+    honoured.  full_batch_once: additionally one timed forward over all 320 graphs of the workload."""
     from oracle import qagnn_oracle as O
     ncpu = os.cpu_count() or 1
-    sd = O.random_state_dict(CFG["k"], CFG["D"], CFG["T"], CFG["R"], "prod", seed)
-    # torch's intra-op pool degrades badly when oversubscribed on many-core hosts: probe a few pool sizes on a
-    # small slice and keep the fastest ("all the host threads it can use")
-    probe = O.synth_graph_batch(8, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
-    best = (float("inf"), 1)
-    for nt in sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu}):
-        torch.set_num_threads(nt)
-        O.message_passing_forward(sd, probe["H"], probe["edge_index"], probe["edge_type"], probe["node_type"],
-                                  probe["node_score"], 1, CFG["T"], CFG["R"], CFG["H"])
-        t0 = time.perf_counter()
-        O.message_passing_forward(sd, probe["H"], probe["edge_index"], probe["edge_type"], probe["node_type"],
-                                  probe["node_score"], 1, CFG["T"], CFG["R"], CFG["H"])
-        best = min(best, (time.perf_counter() - t0, nt))
-    cores = best[1]
+    cores = min(CPU_THREADS, ncpu)
     torch.set_num_threads(cores)
+    sd = O.random_state_dict(CFG["k"], CFG["D"], CFG["T"], CFG["R"], "prod", seed)
+    probe = O.synth_graph_batch(8, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
+
+    def fwd(inp, k):
+        return O.message_passing_forward(sd, inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"], inp["node_score"], k,
+                                         CFG["T"], CFG["R"], CFG["H"])
+    fwd(probe, 1)  # warms the pool and the allocator
+    t0 = time.perf_counter()
+    fwd(probe, 1)
+    per_graph = (time.perf_counter() - t0) / 8 * CFG["k"]  # seconds per graph and forward
     if budget_s is not None:
-        per_graph = best[0] / 8 * CFG["k"]          # probe = 8 graphs, 1 layer
         sample_graphs = int(max(4, min(sample_graphs, budget_s / ((steps + warmup) * per_graph))))
     inp = O.synth_graph_batch(sample_graphs, CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
     E = inp["edge_index"].size(1)
-
-    def step():
-        return O.message_passing_forward(sd, inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"],
-                                         inp["node_score"], CFG["k"], CFG["T"], CFG["R"], CFG["H"])
     for _ in range(warmup):
-        step()
+        fwd(inp, CFG["k"])
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        fwd(inp, CFG["k"])
     dt = (time.perf_counter() - t0) / steps
-    return {"value": CFG["k"] * E / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_graphs} of the {CFG['graphs']} graphs of the workload ({E} edges), {steps} timed "
-                      f"forwards of the op-for-op oracle port (torch CPU fp32, {cores} threads = fastest pool size of those probed on "
-                      f"this {ncpu}-cpu host), {dt * 1e3:.1f} ms each",
-            "ms_per_step": dt * 1e3}
+    res = {"value": CFG["k"] * E / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{sample_graphs} of the {CFG['graphs']} graphs of the workload ({E} edges), {steps} timed "
+                     f"forwards of the op-for-op oracle port (torch CPU fp32, {cores} threads pinned, {ncpu}-cpu host), "
+                     f"{dt * 1e3:.1f} ms each",
+           "ms_per_step": dt * 1e3}
+    if full_batch_once:
+        full = O.synth_graph_batch(CFG["graphs"], CFG["n"], CFG["e"], CFG["D"], CFG["R"], seed)
+        t0 = time.perf_counter()
+        fwd(full, CFG["k"])
+        dtf = time.perf_counter() - t0
+        Ef = full["edge_index"].size(1)
+        res["full_batch"] = {"value": CFG["k"] * Ef / dtf, "unit": UNIT, "ms": dtf * 1e3,
+                             "sample": f"all {CFG['graphs']} graphs ({Ef} edges), one timed forward, {cores} threads"}
+    return res
 
 
 def oracle_slice(inp, sd, g0, count):
@@ -386,9 +392,19 @@ def run_b200_arm(args):
     for v in stages.values():
         v["share"] = v["ms_per_step"] / stage_total
 
-    if rank != 0:
+    def finish():
+        """Leaves the job without tearing NCCL down: the captured CUDA graphs hold NCCL kernels, and destroying the
+        communicator under them hung the 2-GPU run at exit (profiles/README.md).  Everybody meets at a last barrier, then
+        each process exits on its own."""
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -432,11 +448,10 @@ def run_b200_arm(args):
                                    "api": "round 1's definition: StreamedRunner around the bare QAGNN_Message_Passing.forward, the "
                                           "[B,n,D] node output downloaded every step"}
     if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N=1 only
-        r = cpu_reference_run(3, 1, args.cpu_sample_graphs)
-        line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+        r = cpu_reference_run(3, 1, args.cpu_sample_graphs, full_batch_once=True)
+        line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "full_batch")}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
