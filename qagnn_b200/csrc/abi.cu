@@ -2,6 +2,7 @@
 // GATConvE (modeling/modeling_qagnn.py:411-484) and QAGNN_Message_Passing (modeling_qagnn.py:53-95).
 #include <atomic>
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -14,8 +15,9 @@ static thread_local char g_cuda_err[256] = "";
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int32_t cuda_fail(cudaError_t e) {
-  strncpy(g_cuda_err, cudaGetErrorString(e), sizeof(g_cuda_err) - 1);
+int32_t cuda_fail(cudaError_t e, const char* file, int line) {
+  const char* base = strrchr(file, '/');
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s:%d)", cudaGetErrorString(e), base ? base + 1 : file, line);
   return QAGNN_ERR_CUDA;
 }
 
@@ -73,6 +75,8 @@ WorkLayout make_work_layout(const qagnn_shape& s) {
   W.mp_hi = take(half); W.mp_lo = take(half);
   const size_t sbh = N * (size_t)round_up8((int)(D / 2)) / 2 + 8;  // one bf16 plane [N, KSh], in floats
   W.sb_hi = take(sbh); W.sb_lo = take(sbh);
+  const size_t xsh = N * (size_t)round_up8((int)(D + D / 2)) / 2 + 8;  // one bf16 plane [N, KS], in floats
+  for (int i = 0; i < 3; ++i) { W.xs_hi[i] = take(xsh); W.xs_lo[i] = take(xsh); }
   const size_t Eps = (Ep + 3) / 4 * 4;  // per-head stride of the tiled path
   W.score = take(Eps * H);
   W.alpha = take(Eps * H);
@@ -115,6 +119,20 @@ __global__ void sin_basis_planes_kernel(int64_t N, int Dh, int ld, const float* 
     l2.x = __float2bfloat16_rn(a - __bfloat162float(h2.x)); l2.y = __float2bfloat16_rn(b - __bfloat162float(h2.y));
     *reinterpret_cast<__nv_bfloat162*>(hi + v * ld + j) = h2;
     *reinterpret_cast<__nv_bfloat162*>(lo + v * ld + j) = l2;
+  }
+}
+
+// copies `w4` 8-byte words per row (a column block of bf16 planes with row stride `ld8` words) from one hi/lo plane pair into
+// two others: score_emb is layer-invariant and has to sit next to x in every [x | score_emb] operand buffer
+__global__ void copy_plane_columns_kernel(int64_t N, int w4, int ld8, const uint2* __restrict__ sh, const uint2* __restrict__ sl,
+                                          uint2* __restrict__ d1h, uint2* __restrict__ d1l, uint2* __restrict__ d2h,
+                                          uint2* __restrict__ d2l) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * w4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / w4;
+    const int c = (int)(i - r * w4);
+    const uint2 h = sh[r * ld8 + c], l = sl[r * ld8 + c];
+    d1h[r * ld8 + c] = h; d1l[r * ld8 + c] = l;
+    d2h[r * ld8 + c] = h; d2l[r * ld8 + c] = l;
   }
 }
 
@@ -257,6 +275,7 @@ bool use_tc(const qagnn_shape& s) { return gemm_tc_available() && s.D % 8 == 0; 
 struct Planes {
   const void* hi;
   const void* lo;
+  int ld = 0;  // row stride in elements; 0 = D
 };
 
 // one GATConvE layer on split-bf16 planes.  x / extra are [N, D] plane pairs; the layer output goes to any of
@@ -264,26 +283,28 @@ struct Planes {
 int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLayout& W, int layer, Planes x, Planes extra,
                          const void* prep, const qagnn_prep_layout& pl, const float* folded, float* out_f32,
                          void* out_hi, void* out_lo, float* alpha_out, float* aggr_out, float* ws, Act final_act,
-                         bool tiled, cudaStream_t st, const int64_t* type_bias_classes = nullptr) {
+                         bool tiled, cudaStream_t st, const int64_t* type_bias_classes = nullptr, int out_ldp = 0) {
   const int D = s.D;
+  if (out_ldp == 0) out_ldp = D;
   const float* lb = folded + L.layer0 + (size_t)layer * L.layer_stride;
   float* qkm = ws + W.qkm;
   const bool fused_split = tiled && (D / s.H) % 2 == 0;  // the tiled kernel emits the bf16 planes of aggr itself
   float* aggr = aggr_out ? aggr_out : (fused_split ? nullptr : ws + W.aggr);
   {  // Q | Kx | Mx = [x ‖ extra] @ Wp^T + bp                     (:440, :464-466 node part, :469)
     ProfScope ps(QAGNN_PROF_PROJECTION, st);
-    TcOperand A1{x.hi, x.lo, D, D}, A2{extra.hi, extra.lo, D, D};
+    TcOperand A1{x.hi, x.lo, x.ld ? x.ld : D, D}, A2{extra.hi, extra.lo, D, D};
     TcOutput o{};
     if (tiled && type_bias_classes != nullptr) {
-      // fast form (qagnn_mp_forward): `extra` holds only score_emb (K = D/2); the type-embedding half of node_feature_extra
-      // enters as a per-node-type bias row (T distinct rows), so the GEMM runs K = D + D/2 instead of 2D
+      // fast form (qagnn_mp_forward): x planes are [N, KS] rows of [x | score_emb] (K = D + D/2, ONE segment); the
+      // type-embedding half of node_feature_extra enters as a per-node-type bias row (T distinct rows).  One segment lets
+      // the GEMM keep its weight tile resident in shared memory (gemm_tc.cu, W-resident variant)
       const int DP = head_dim_padded(D / s.H), KS = round_up8(D + D / 2);
-      TcOperand A2s{extra.hi, extra.lo, D, D / 2};
+      TcOperand Ax{x.hi, x.lo, KS, D + D / 2}, none{nullptr, nullptr, 0, 0};
       TcOperand Wp{lb + L.wps_hi, lb + L.wps_lo, KS, D + D / 2};
       o.hm_buf = qkm;
       o.hm = HeadMajorOut{1, D, D / s.H, DP, s.H};
       o.row_class = type_bias_classes; o.class_stride = 3 * s.H * DP; o.n_class = s.T;
-      QAGNN_RETURN_IF(gemm_tc(A1, A2s, Wp, lb + L.tbias, s.N, 3 * s.H * DP, ACT_NONE, o, st));
+      QAGNN_RETURN_IF(gemm_tc(Ax, none, Wp, lb + L.tbias, s.N, 3 * s.H * DP, ACT_NONE, o, st));
     } else if (tiled) {  // per-head padded weight rows -> the GEMM writes [3][H][N][DP] (pads = exact zeros) itself
       const int DP = head_dim_padded(D / s.H);
       TcOperand Wp{lb + L.wph_hi, lb + L.wph_lo, 2 * D, 2 * D};
@@ -321,7 +342,7 @@ int32_t layer_forward_tc(const qagnn_shape& s, const FoldLayout& L, const WorkLa
     QAGNN_RETURN_IF(gemm_tc(A, none, W1, lb + L.b1, s.N, D, ACT_RELU, o1, st));
     TcOperand Hm{ws + W.mp_hi, ws + W.mp_lo, D, D};
     TcOutput o2{};
-    o2.f32 = out_f32; o2.ldc = D; o2.hi = out_hi; o2.lo = out_lo; o2.ldp = D;
+    o2.f32 = out_f32; o2.ldc = D; o2.hi = out_hi; o2.lo = out_lo; o2.ldp = out_ldp;
     QAGNN_RETURN_IF(gemm_tc(Hm, none, W2, lb + L.b2, s.N, D, final_act, o2, st));
   }
   return QAGNN_OK;
@@ -465,21 +486,55 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
   // fast form: tensor-core emb_score + type-embedding half of node_feature_extra folded into per-type bias rows
   // (QAGNN_MP_FASTPROJ=0 keeps the general [x | extra] projection, for A/B runs and tests)
   const char* efp = getenv("QAGNN_MP_FASTPROJ");
-  const bool fast = tc && tiled && s.k > 0 && (s.D / 2) % 2 == 0 && !(efp && atoi(efp) == 0);
+  const bool fast = tc && tiled && s.k > 0 && (s.D / 2) % 4 == 0 && !(efp && atoi(efp) == 0);
   if (fast) {
+    const int D = s.D, Dh = D / 2, KSh = round_up8(Dh), KS = round_up8(D + Dh);
+    char* xh[3]; char* xl[3];
+    for (int i = 0; i < 3; ++i) { xh[i] = (char*)(ws + W.xs_hi[i]); xl[i] = (char*)(ws + W.xs_lo[i]); }
+    {
+      ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
+      int64_t g = (s.N * (Dh / 2) + 255) / 256;
+      if (g > 148 * 32) g = 148 * 32;
+      sin_basis_planes_kernel<<<(unsigned)g, 256, 0, st>>>(s.N, Dh, KSh, node_score, f + L.basis, (__nv_bfloat16*)(ws + W.sb_hi),
+                                                           (__nv_bfloat16*)(ws + W.sb_lo));
+      QAGNN_CHECK_LAUNCH();
+      // score_emb = GELU(emb_score(sin basis)) -> columns [D, D + D/2) of the H_in planes                   (:73)
+      TcOperand A{ws + W.sb_hi, ws + W.sb_lo, KSh, Dh}, none{nullptr, nullptr, 0, 0}, Wsc{f + L.ws_hi, f + L.ws_lo, KSh, Dh};
+      TcOutput o{};
+      o.hi = xh[0] + (size_t)D * 2; o.lo = xl[0] + (size_t)D * 2; o.ldp = KS;
+      QAGNN_RETURN_IF(gemm_tc(A, none, Wsc, f + L.bs, s.N, Dh, ACT_GELU, o, st));
+      // ... and into the two activation buffers (layer-invariant: modeling_qagnn.py:86)
+      {
+        const int w4 = Dh * 2 / 8, ld8 = KS * 2 / 8;  // Dh % 4 == 0 and KS % 8 == 0 (checked by `fast`)
+        int64_t gc = (s.N * w4 + 255) / 256;
+        if (gc > 148 * 16) gc = 148 * 16;
+        const size_t off = (size_t)D * 2;
+        copy_plane_columns_kernel<<<(unsigned)gc, 256, 0, st>>>(s.N, w4, ld8, (const uint2*)(xh[0] + off), (const uint2*)(xl[0] + off),
+                                                              (uint2*)(xh[1] + off), (uint2*)(xl[1] + off), (uint2*)(xh[2] + off),
+                                                              (uint2*)(xl[2] + off));
+        QAGNN_CHECK_LAUNCH();
+      }
+      QAGNN_RETURN_IF(split_bf16(H_in, D, s.N, D, xh[0], xl[0], KS, st));
+    }
+    const size_t ND = (size_t)s.N * s.D;
+    Planes xin{xh[0], xl[0], KS};
+    const Planes ep{nullptr, nullptr, 0};
+    for (int l = 0; l < s.k; ++l) {  // mp_helper, :45-50 (dropout is the identity in eval)
+      float* xo32 = x_layers_out ? x_layers_out + (size_t)l * ND : nullptr;
+      void* ohi = xh[1 + (l & 1)];
+      void* olo = xl[1 + (l & 1)];
+      QAGNN_RETURN_IF(layer_forward_tc(s, L, W, l, xin, ep, prep, pl, f, xo32, ohi, olo, nullptr, nullptr, ws, ACT_GELU, tiled, st,
+                                       node_type, KS));
+      xin = Planes{ohi, olo, KS};
+    }
+    // output = GELU(Vh(H) + Vx(X))                                           (:92)
     ProfScope ps(QAGNN_PROF_PRO_EPILOGUE, st);
-    const int Dh = s.D / 2, KSh = round_up8(Dh);
-    int64_t g = (s.N * (Dh / 2) + 255) / 256;
-    if (g > 148 * 32) g = 148 * 32;
-    sin_basis_planes_kernel<<<(unsigned)g, 256, 0, st>>>(s.N, Dh, KSh, node_score, f + L.basis, (__nv_bfloat16*)(ws + W.sb_hi),
-                                                         (__nv_bfloat16*)(ws + W.sb_lo));
-    QAGNN_CHECK_LAUNCH();
-    // score_emb = GELU(emb_score(sin basis)) -> columns [0, D/2) of the `extra` planes               (:73)
-    TcOperand A{ws + W.sb_hi, ws + W.sb_lo, KSh, Dh}, none{nullptr, nullptr, 0, 0}, Wsc{f + L.ws_hi, f + L.ws_lo, KSh, Dh};
+    TcOperand A1{xh[0], xl[0], KS, D}, A2{xin.hi, xin.lo, KS, D}, Wv{f + L.vcat_hi, f + L.vcat_lo, 2 * D, 2 * D};
     TcOutput o{};
-    o.hi = ws + W.ep_hi; o.lo = ws + W.ep_lo; o.ldp = s.D;
-    QAGNN_RETURN_IF(gemm_tc(A, none, Wsc, f + L.bs, s.N, Dh, ACT_GELU, o, st));
-  } else {
+    o.f32 = out; o.ldc = D;
+    return gemm_tc(A1, A2, Wv, f + L.vbias, s.N, D, ACT_GELU, o, st);
+  }
+  {
     // tensor-core path: `extra` is only ever consumed as split-bf16 planes, so the prologue writes those directly
     QAGNN_RETURN_IF(extra_forward(s, L, W, node_type, node_score, f, tc && s.D / 2 <= 128 ? nullptr : extra, ws, st,
                                   tc ? ws + W.ep_hi : nullptr, tc ? ws + W.ep_lo : nullptr));
@@ -499,7 +554,7 @@ extern "C" int32_t qagnn_mp_forward(const qagnn_shape* shape, const float* H_in,
       void* ohi = ws + W.xp_hi[l & 1];
       void* olo = ws + W.xp_lo[l & 1];
       QAGNN_RETURN_IF(layer_forward_tc(s, L, W, l, xin, ep, prep, pl, f, xo32, ohi, olo, nullptr, nullptr, ws, ACT_GELU,
-                                       tiled, st, fast ? node_type : nullptr));
+                                       tiled, st));
       xin = Planes{ohi, olo};
     }
     // output = GELU(Vh(H) + Vx(X))                                           (:92)

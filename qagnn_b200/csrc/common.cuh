@@ -14,19 +14,19 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a = kAlign) { return
 
 // ---- launch bookkeeping -------------------------------------------------------------------------
 void note_launch(int n = 1);
-int32_t cuda_fail(cudaError_t e);  // records the error text, returns QAGNN_ERR_CUDA
+int32_t cuda_fail(cudaError_t e, const char* file, int line);  // records the error text + call site, returns QAGNN_ERR_CUDA
 
 #define QAGNN_CHECK_LAUNCH()                               \
   do {                                                     \
     cudaError_t e__ = cudaGetLastError();                  \
-    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__);\
+    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__, __FILE__, __LINE__);\
     ::qagnn::note_launch();                                \
   } while (0)
 
 #define QAGNN_CHECK_CUDA(expr)                              \
   do {                                                     \
     cudaError_t e__ = (expr);                              \
-    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__);\
+    if (e__ != cudaSuccess) return ::qagnn::cuda_fail(e__, __FILE__, __LINE__);\
   } while (0)
 
 #define QAGNN_RETURN_IF(st)        \
@@ -109,6 +109,7 @@ struct WorkLayout {
   size_t ap_hi, ap_lo;          // aggr
   size_t mp_hi, mp_lo;          // mlp hidden
   size_t sb_hi, sb_lo;          // sin basis [N, KSh] planes (A operand of emb_score on the tensor-core path)
+  size_t xs_hi[3], xs_lo[3];    // fast projection: [x | score_emb] planes [N, KS] (0: H_in, 1/2: layer activations, ping-pong)
   size_t score;   // [E', H]  raw logits / exp scratch (by-source order)
   size_t alpha;   // [E', H]  out-degree-scaled softmax (by-source order; general CSR path)
   size_t alpha2;  // [H, E'] x 2 words  tiled path: {row offsets, a'} per edge and head in by-target order

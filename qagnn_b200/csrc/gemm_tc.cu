@@ -17,6 +17,7 @@
 // the ~30x slower FFMA path (sgemm.cu, kept as the exact-fp32 fallback).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -41,6 +42,7 @@ struct alignas(64) TcParams {
   CUtensorMap o_f32, o_hm, o_hi, o_lo;  // TMA-store maps of the requested outputs
   int nseg, kseg[2];
   int umma_n, n_step, N, stages;
+  int nkb_total;  // k blocks of the (single) A segment: rows of the resident weight region (W-resident variant)
   long long M;
   const float* bias;
   const int64_t* row_class;  // optional: bias row = clamp(row_class[r], 0, n_class-1) * class_stride
@@ -183,23 +185,32 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive o
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-template <int ACT, int BK, int CTAS>
+// WRES = true ("W-resident"): one A segment, and a CTA pair works on ONE n tile for the whole launch, so its share of the
+// weight tile for ALL k blocks (umma_n/2 rows x K, hi + lo planes: 133 KB for the K = 300 projection, 115 KB for the K = 200
+// node MLP) is loaded once and stays in shared memory; the ring then carries only A (32 KB per stage instead of ~59 KB).
+// The streamed variant moved 607 MB through L2 -> SM per projection with the tensor pipe 38 % active and nothing
+// saturated (profiles/r2_gemm_ncu.md): the ring was latency bound, and most of its bytes were weights re-fetched per tile.
+template <int ACT, int BK, int CTAS, bool WRES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 2;              // one A plane tile: 16 KB
   const uint32_t wn = (uint32_t)p.umma_n / CTAS;     // W rows this CTA stages
-  const uint32_t w_bytes = wn * BK * 2;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  const uint32_t w_bytes = wn * BK * 2;              // one W plane k-block
+  const uint32_t stage_bytes = WRES ? 2 * a_bytes : 2 * a_bytes + 2 * w_bytes;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const unsigned cl_id = blockIdx.x / CTAS, n_cl = gridDim.x / CTAS;  // cluster index / count (tile scheduler)
-  unsigned char* ctrl = smem + (size_t)p.stages * stage_bytes;
+  // resident weights (WRES): [k block][hi | lo][wn rows x 128 B], after the ring
+  const uint32_t wres_bytes = WRES ? (uint32_t)p.nkb_total * 2u * w_bytes : 0u;
+  unsigned char* wres = smem + (size_t)p.stages * stage_bytes;
+  unsigned char* ctrl = wres + wres_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);       // [stages]  TMA -> MMA
   uint64_t* empty = full + p.stages;                        // [stages]  MMA -> TMA
   uint64_t* acc_full = empty + p.stages;                    // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;                       // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* wfull = acc_empty + 2;                          // [1]       resident weights landed (WRES)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   // k-blocks across the (up to two) A segments
   int nkb_seg[2];
@@ -209,6 +220,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int n_tiles = (p.N + p.n_step - 1) / p.n_step;
   const long long m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS);
   const long long total_tiles = m_tiles * n_tiles;
+  // tile walk of this cluster.  Streamed: tile = cl_id, cl_id + n_cl, ... over (m, n) with n fastest.  W-resident: the
+  // cluster keeps n tile cl_id % n_tiles and walks the m tiles idx, idx + cnt, ... of the clusters that share it.
+  const int my_n = WRES ? (int)(cl_id % (unsigned)n_tiles) : 0;
+  const long long w_idx = cl_id / (unsigned)n_tiles;
+  const long long w_cnt = WRES ? ((long long)n_cl - my_n + n_tiles - 1) / n_tiles : 1;
+  const long long t_first = WRES ? w_idx * n_tiles + my_n : (long long)cl_id;
+  const long long t_step = WRES ? w_cnt * n_tiles : (long long)n_cl;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -219,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], kEpiWarps * CTAS);  // one arrival per epilogue warp (of both CTAs: only the leader's copy is used)
     }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {  // TMEM allocation is warp-collective; the same warp frees it
@@ -240,7 +259,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       long long it = 0;  // k-block counter across tiles
-      for (long long tile = cl_id; tile < total_tiles; tile += n_cl) {
+      if (WRES && t_first < total_tiles) {  // this CTA's rows of the n tile, every k block, once
+        const int n0 = my_n * p.n_step + (int)(rank * wn);
+        if (CTAS == 1) mbar_expect_tx(wfull, wres_bytes);
+        else if (leader) mbar_expect_tx(wfull, 2 * wres_bytes);
+        for (int kb = 0; kb < nkb; ++kb) {
+          unsigned char* dst = wres + (size_t)kb * 2 * w_bytes;
+          if (CTAS == 1) {
+            tma_load_2d(dst, &p.w_hi, kb * BK, n0, wfull);
+            tma_load_2d(dst + w_bytes, &p.w_lo, kb * BK, n0, wfull);
+          } else {
+            tma_load_2d_2sm(dst, &p.w_hi, kb * BK, n0, wfull);
+            tma_load_2d_2sm(dst + w_bytes, &p.w_lo, kb * BK, n0, wfull);
+          }
+        }
+      }
+      for (long long tile = t_first; tile < total_tiles; tile += t_step) {
         const int n0 = (int)(tile % n_tiles) * p.n_step + (int)(rank * wn);
         const int m0 = (int)((tile / n_tiles) * BM * CTAS + rank * BM);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -250,7 +284,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int k_in_seg = (seg == 0 ? kb : kb - nkb_seg[0]) * BK;
           const int k_glob = (seg == 0 ? 0 : p.kseg[0]) + k_in_seg;
           unsigned char* st = smem + (size_t)s * stage_bytes;
-          if (CTAS == 1) {
+          if (WRES) {
+            if (CTAS == 1) {
+              mbar_expect_tx(&full[s], stage_bytes);
+              tma_load_2d(st, &p.a_hi[0], k_in_seg, m0, &full[s]);
+              tma_load_2d(st + a_bytes, &p.a_lo[0], k_in_seg, m0, &full[s]);
+            } else {
+              if (leader) mbar_expect_tx(&full[s], 2 * stage_bytes);
+              tma_load_2d_2sm(st, &p.a_hi[0], k_in_seg, m0, &full[s]);
+              tma_load_2d_2sm(st + a_bytes, &p.a_lo[0], k_in_seg, m0, &full[s]);
+            }
+          } else if (CTAS == 1) {
             mbar_expect_tx(&full[s], stage_bytes);
             tma_load_2d(st, &p.a_hi[seg], k_in_seg, m0, &full[s]);
             tma_load_2d(st + a_bytes, &p.a_lo[seg], k_in_seg, m0, &full[s]);
@@ -273,7 +317,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.umma_n >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
       long long it = 0;
       int ti = 0;
-      for (long long tile = cl_id; tile < total_tiles; tile += n_cl, ++ti) {
+      if (WRES && t_first < total_tiles) {
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+      }
+      for (long long tile = t_first; tile < total_tiles; tile += t_step, ++ti) {
         const int acc = ti & 1;
         if (ti >= 2) {  // the epilogue must have drained this accumulator
           mbar_wait(&acc_empty[acc], (uint32_t)((ti >> 1) - 1) & 1u);
@@ -291,7 +339,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           for (int k = 0; k < nsteps; ++k) {
             const uint64_t da_hi = umma_desc<BK>(sa + k * 32), da_lo = umma_desc<BK>(sa + a_bytes + k * 32);
-            const uint64_t dw_hi = umma_desc<BK>(sa + 2 * a_bytes + k * 32), dw_lo = umma_desc<BK>(sa + 2 * a_bytes + w_bytes + k * 32);
+            const uint32_t sw = WRES ? smem_u32(wres + (size_t)kb * 2 * w_bytes) : sa + 2 * a_bytes;
+            const uint64_t dw_hi = umma_desc<BK>(sw + k * 32), dw_lo = umma_desc<BK>(sw + w_bytes + k * 32);
             if (CTAS == 1) {
               umma_bf16(tmem_d, da_hi, dw_hi, idesc, (kb | k) != 0);
               umma_bf16(tmem_d, da_hi, dw_lo, idesc, 1u);
@@ -315,13 +364,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // one cp.async.bulk.tensor store per 32x32 block.  TMA clips rows >= M and columns past the tensor, so there are
     // no bound checks; the store drains asynchronously while the warp loads the next block from TMEM.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read (warp id % 4)
-    unsigned char* stg = smem + (size_t)p.stages * stage_bytes + 1024 + (size_t)warp * kStageBytesPerWarp;
+    unsigned char* stg = ctrl + 1024 + (size_t)warp * kStageBytesPerWarp;
     const bool hm_mode = p.c_hm != nullptr;
     const int DP = hm_mode ? p.hm.DP : 0;
     const int per_head = hm_mode ? (DP + 31) / 32 : 0;                      // 32-column blocks per head slab
     const int nblk = hm_mode ? p.hm.H * per_head : (p.n_step + 31) / 32;    // blocks per tile
     int ti = 0;
-    for (long long tile = cl_id; tile < total_tiles; tile += n_cl, ++ti) {
+    for (long long tile = t_first; tile < total_tiles; tile += t_step, ++ti) {
       const int acc = ti & 1;
       const int n_tile = (int)(tile % n_tiles);
       const int n0 = n_tile * p.n_step;
@@ -547,13 +596,34 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   const char* e2 = getenv("QAGNN_TC_2CTA");
   const int CTAS = (e2 && atoi(e2) == 0) ? 1 : 2;
   constexpr int BK = 64;
-  const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)(p.umma_n / CTAS) * BK * 2;
-  int stages = (int)((226 * 1024 - 1024 - kEpiWarps * kStageBytesPerWarp) / stage_bytes);
+  const size_t smem_cap = 227 * 1024, epi_bytes = kEpiWarps * (size_t)kStageBytesPerWarp;
+  const size_t w_blk = (size_t)(p.umma_n / CTAS) * BK * 2;  // one plane, one k block, this CTA's rows
+  // W-resident variant: single A segment, 2-CTA tiles, enough pairs for every n tile, and the CTA's share of the weight
+  // tile for all k blocks must leave room for at least two A stages.  QAGNN_TC_WRES=0 keeps the streamed variant.
+  const int nkb1 = (K1 + BK - 1) / BK;
+  // Measured at cfg2 (profiles/r2_gemm_ncu.md): 85 vs 80 us for the K = 300 projection, 74 vs 71 us per node MLP — with the
+  // weights resident only two A stages fit, and the ring is bound by its depth, not by its bytes.  Opt-in: QAGNN_TC_WRES=1.
+  const char* ewr = getenv("QAGNN_TC_WRES");
+  bool wres = K2 == 0 && CTAS == 2 && (ewr && atoi(ewr) == 1);
+  size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * w_blk;
+  size_t wres_bytes = 0;
+  int stages = 0;
+  if (wres) {
+    wres_bytes = (size_t)nkb1 * 2 * w_blk;
+    const size_t a_stage = 2 * (size_t)BM * BK * 2;
+    if (wres_bytes + 2 * a_stage + 1024 + epi_bytes > smem_cap) { wres = false; wres_bytes = 0; }
+    else {
+      stage_bytes = a_stage;
+      stages = (int)((smem_cap - 1024 - epi_bytes - wres_bytes) / a_stage);
+    }
+  }
+  if (!wres) stages = (int)((226 * 1024 - 1024 - epi_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return QAGNN_ERR_UNSUPPORTED;
   p.stages = stages;
-  // operand ring | 1 KB of barriers | 4 per-warp transpose buffers
-  const size_t smem_bytes = stages * stage_bytes + 1024 + kEpiWarps * (size_t)kStageBytesPerWarp;
+  p.nkb_total = nkb1;
+  // operand ring | resident weights (W-resident variant) | 1 KB of barriers | per-warp transpose buffers
+  const size_t smem_bytes = stages * stage_bytes + wres_bytes + 1024 + epi_bytes;
   bool ok = make_map(&p.a_hi[0], A1.hi, M, K1, A1.ld, BM, BK) && make_map(&p.a_lo[0], A1.lo, M, K1, A1.ld, BM, BK);
   if (K2 > 0) ok = ok && make_map(&p.a_hi[1], A2.hi, M, K2, A2.ld, BM, BK) && make_map(&p.a_lo[1], A2.lo, M, K2, A2.ld, BM, BK);
   ok = ok && make_map(&p.w_hi, W.hi, N, K1 + K2, W.ld, p.umma_n / CTAS, BK) &&
@@ -583,12 +653,16 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   static size_t attr_c[kMaxDevices] = {0};  // the attribute is per device
   const int dev_i = current_device();
   size_t& attr = attr_c[dev_i];
-  if (smem_bytes > attr) {
+  if (attr == 0) {
 #define QAGNN_SET_ATTR(A, B, Cn) \
-  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B, Cn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes))
+  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, B, Cn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)))
     QAGNN_SET_ATTR(ACT_NONE, 64, 1); QAGNN_SET_ATTR(ACT_RELU, 64, 1); QAGNN_SET_ATTR(ACT_GELU, 64, 1);
     QAGNN_SET_ATTR(ACT_NONE, 64, 2); QAGNN_SET_ATTR(ACT_RELU, 64, 2); QAGNN_SET_ATTR(ACT_GELU, 64, 2);
 #undef QAGNN_SET_ATTR
+#define QAGNN_SET_ATTR_W(A) \
+  QAGNN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A, 64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap))
+    QAGNN_SET_ATTR_W(ACT_NONE); QAGNN_SET_ATTR_W(ACT_RELU); QAGNN_SET_ATTR_W(ACT_GELU);
+#undef QAGNN_SET_ATTR_W
     attr = smem_bytes;
   }
   static int sms_c[kMaxDevices] = {0};
@@ -596,6 +670,7 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   const int sms = sms_c[dev_i];
   const long long total_tiles = (long long)n_tiles * ((M + (long long)BM * CTAS - 1) / ((long long)BM * CTAS));
   long long units = total_tiles < sms / CTAS ? total_tiles : sms / CTAS;  // CTAs (or CTA pairs) to launch
+  if (wres && units < n_tiles) units = n_tiles;  // every n tile needs a pair that keeps its weights
   const unsigned grid = (unsigned)(units * CTAS);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -610,10 +685,12 @@ int32_t gemm_tc(const TcOperand& A1, const TcOperand& A2, const TcOperand& W, co
   lattr[0].val.clusterDim.z = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  if (getenv("QAGNN_DEBUG")) fprintf(stderr, "gemm_tc: M=%lld N=%d K1=%d K2=%d act=%d wres=%d CTAS=%d stages=%d smem=%zu grid=%u umma_n=%d n_tiles=%d\n", M, N, K1, K2, (int)act, (int)wres, CTAS, stages, smem_bytes, grid, p.umma_n, n_tiles);
 #define QAGNN_LAUNCH(A)                                                                          \
   do {                                                                                           \
-    if (CTAS == 2) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 2>, p));       \
-    else QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 1>, p));                 \
+    if (wres) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 2, true>, p));               \
+    else if (CTAS == 2) QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 2, false>, p));    \
+    else QAGNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A, 64, 1, false>, p));                   \
   } while (0)
   if (act == ACT_NONE) QAGNN_LAUNCH(ACT_NONE);
   else if (act == ACT_RELU) QAGNN_LAUNCH(ACT_RELU);

@@ -268,7 +268,7 @@ def test_bench_workload_matches_oracle_on_first_middle_and_last_graphs():
 # ---- every launch-time switch the shipped library keeps (read at each call) has GPU coverage ------------------------
 @pytest.mark.parametrize("env", [{"QAGNN_MP_PATH": "csr"}, {"QAGNN_MP_PATH": "basic"}, {"QAGNN_TC_2CTA": "0"}, {"QAGNN_GEMM": "ffma"},
                                  {"QAGNN_MP_WARPS": "24"}, {"QAGNN_MP_WARPS": "31"}, {"QAGNN_MP_WARPS": "7"},
-                                 {"QAGNN_MP_FASTPROJ": "0"}])
+                                 {"QAGNN_MP_FASTPROJ": "0"}, {"QAGNN_TC_WRES": "1"}])
 @pytest.mark.parametrize("name", ["cfg2small_peaky", "cfg2small_realistic", "tiny_realistic_d100", "no_edges"])
 def test_goldens_under_every_kept_switch(name, env, monkeypatch):
     for k_, v in env.items():
