@@ -83,11 +83,19 @@ def load():
         return _lib
     from . import build as _build
     if os.path.exists(LIB_PATH) and not _build.is_current():
-        # sources changed since the library was built: rebuild when a compiler is around, never run stale code
-        try:
-            _build.build()
-        except Exception as e:  # noqa: BLE001
-            raise RuntimeError(f"{LIB_PATH} is older than qagnn_b200/csrc and could not be rebuilt: {e}") from e
+        # sources changed since the library was built: rebuild when a compiler is around, never run stale code.  Under
+        # torchrun every rank gets here at once: one rebuilds under an exclusive file lock, the others wait and re-check.
+        import fcntl
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        with open(LIB_PATH + ".lock", "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if not _build.is_current():
+                    _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(f"{LIB_PATH} is older than qagnn_b200/csrc and could not be rebuilt: {e}") from e
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: the qagnn_b200 CUDA library has not been built. Run "

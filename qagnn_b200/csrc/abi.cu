@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/qagnn_b200.h: the forward orchestration of
 // GATConvE (modeling/modeling_qagnn.py:411-484) and QAGNN_Message_Passing (modeling_qagnn.py:53-95).
 #include <atomic>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,10 +32,13 @@ struct ProfState {
   int created = 0;
   int stage[kProfMax];
   int open_idx[QAGNN_PROF_STAGES];
+  std::mutex mu;  // the stage timers are process-wide diagnostics: calls from several host threads serialise here
 } g_prof;
 }  // namespace
 
 void prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof.on) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   if (!g_prof.on || g_prof.n >= kProfMax) { if (g_prof.on) g_prof.open_idx[stage] = -1; return; }
   const int i = g_prof.n++;
   if (i >= g_prof.created) {
@@ -49,6 +53,7 @@ void prof_begin(int stage, cudaStream_t st) {
 
 void prof_end(int stage, cudaStream_t st) {
   if (!g_prof.on) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   const int i = g_prof.open_idx[stage];
   if (i >= 0) cudaEventRecord(g_prof.ev[i][1], st);
 }
@@ -404,6 +409,7 @@ extern "C" const char* qagnn_last_cuda_error(void) { return g_cuda_err; }
 extern "C" int64_t qagnn_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int32_t qagnn_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   g_prof.on = on != 0;
   g_prof.n = 0;
   for (int i = 0; i < QAGNN_PROF_STAGES; ++i) g_prof.open_idx[i] = -1;
@@ -412,6 +418,7 @@ extern "C" int32_t qagnn_profile_enable(int32_t on) {
 
 extern "C" int32_t qagnn_profile_read(double* ms_out, int64_t* count_out) {
   if (!ms_out || !count_out) return QAGNN_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   for (int i = 0; i < QAGNN_PROF_STAGES; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
   for (int i = 0; i < g_prof.n; ++i) {
     QAGNN_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[i][1]));
