@@ -244,6 +244,46 @@ def mint_train_case(ref, case, n_ntype=4, n_etype=38):
             "grads": grads, "buffers_after": buffers}
 
 
+TRAIN_DEC_CASES = [
+    dict(name="train_decoder_small", B=6, n=30, e=80, D=64, k=2, sent_dim=48, n_concept=500, concept_in_dim=32,
+         n_head=2, n_fc_layer=1, regime="peaky", seed=24),
+]
+
+
+def mint_train_decoder_case(ref, case, n_ntype=4, n_etype=38):
+    """The whole reference decoder (`QAGNN`, modeling_qagnn.py:99-189) in .train(): every nn.Dropout of the instance gets
+    p = 0 (a live mask stream cannot be reproduced), BatchNorm batch statistics, loss = sum(logits * g), autograd."""
+    inp, sent_vecs, concept_ids = build_decoder_inputs(case, n_etype)
+    dec = ref.QAGNN(None, case["k"], n_ntype, n_etype, case["sent_dim"], case["n_concept"], case["D"],
+                    case["concept_in_dim"], case["n_head"], case["D"], case["n_fc_layer"], 0.0, 0.0, 0.0,
+                    pretrained_concept_emb=None, freeze_ent_emb=True, init_range=0.02)
+    sd = decoder_state_dict(dec, case)
+    dec.load_state_dict(sd, strict=True)
+    dec.train()
+    for m in dec.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    dec.gnn.dropout_rate = 0.0
+    sv = sent_vecs.clone().requires_grad_(True)
+    logits, pool_attn = dec(sv, concept_ids, inp["node_type"], inp["node_score"], inp["adj_lengths"],
+                            (inp["edge_index"], inp["edge_type"]))
+    g = torch.Generator().manual_seed(9100 + case["seed"])
+    w = torch.randn(logits.shape, generator=g)
+    loss = (logits * w).sum()
+    loss.backward()
+    grads, seen = {}, set()
+    for name, p_ in dec.named_parameters():
+        if id(p_) in seen:
+            continue
+        seen.add(id(p_))
+        grads[name] = p_.grad.detach().clone() if p_.grad is not None else None
+    return {"kind": "train_decoder", "case": case, "n_ntype": n_ntype, "n_etype": n_etype,
+            "state_dict": {k_: v.clone() for k_, v in sd.items()}, "logits": logits.detach().clone(),
+            "pool_attn": pool_attn.detach().clone(), "loss_weights": w, "loss": float(loss.detach()),
+            "grad_sent": sv.grad.clone(), "grads": grads,
+            "input_fp": fingerprint(inp["H"], inp["edge_index"], sent_vecs, concept_ids)}
+
+
 def main():
     torch.set_num_threads(8)
     ref = load_reference()
@@ -260,6 +300,10 @@ def main():
         fx = mint_train_case(ref, case)
         torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
         print("minted", case["name"], fx["loss"], float(fx["grad_H"].abs().mean()))
+    for case in TRAIN_DEC_CASES:
+        fx = mint_train_decoder_case(ref, case)
+        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
+        print("minted", case["name"], fx["loss"])
     for case in DEC_CASES:
         fx = mint_decoder_case(ref, case)
         torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))

@@ -124,3 +124,37 @@ def test_single_layer_training_gradients_against_autograd_of_the_oracle():
     (out * G.to(DEV)).sum().backward()
     _grad_close(xg.grad, x.grad, "dL/dx")
     _grad_close(eg.grad, extra.grad, "dL/dextra")
+
+
+def test_whole_decoder_training_step_matches_reference():
+    """`QAGNN` (input assembly + message passing + pooling + answer MLP, modeling_qagnn.py:99-189) in .train(): logits, loss and
+    every gradient against the reference's own decoder run under autograd (oracle/make_goldens.py: mint_train_decoder_case)."""
+    fx = Hh.load_golden("train_decoder_small")
+    c = fx["case"]
+    inp, sent_vecs, concept_ids = MG.build_decoder_inputs(c, fx["n_etype"])
+    dec = qagnn_b200.QAGNN(None, c["k"], fx["n_ntype"], fx["n_etype"], c["sent_dim"], c["n_concept"], c["D"], c["concept_in_dim"],
+                           c["n_head"], c["D"], c["n_fc_layer"], 0.0, 0.0, 0.0)
+    dec.load_state_dict(fx["state_dict"], strict=True)
+    dec = dec.to(DEV).train()
+    for m in dec.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    dec.gnn.dropout_rate = 0.0
+    sv = sent_vecs.to(DEV).requires_grad_(True)
+    logits, pool_attn = dec(sv, concept_ids.to(DEV), inp["node_type"].to(DEV), inp["node_score"].to(DEV), inp["adj_lengths"].to(DEV),
+                            (inp["edge_index"].to(DEV), inp["edge_type"].to(DEV)))
+    Hh.assert_close(logits, fx["logits"], "train-mode logits")
+    Hh.assert_close(pool_attn, fx["pool_attn"], "train-mode pool_attn")
+    loss = (logits * fx["loss_weights"].to(DEV)).sum()
+    loss.backward()
+    assert abs(float(loss.detach()) - fx["loss"]) <= 1e-3 + 1e-4 * abs(fx["loss"])
+    _grad_close(sv.grad, fx["grad_sent"], "dL/dsent_vecs")
+    got = dict(dec.named_parameters())
+    assert sorted(got) == sorted(fx["grads"])
+    gmax = max(float(g.abs().max()) for g in fx["grads"].values() if g is not None)
+    for pname, ref_g in fx["grads"].items():
+        if ref_g is None:  # frozen entity embedding (freeze_ent_emb=True)
+            assert got[pname].grad is None, pname
+            continue
+        assert got[pname].grad is not None, pname
+        _grad_close(got[pname].grad, ref_g, f"dL/d{pname}", floor=1e-2 * gmax)
