@@ -53,6 +53,30 @@ __global__ void smem_read(int iters, float* out) {
   if (acc == 123.456f) out[0] = acc;
 }
 
+// The message-passing kernel's access pattern: every quarter-warp (8 lanes) reads one 208-byte row (13 float4 chunks:
+// chunks 0-7, then chunks 8-12 with lanes 5-7 re-reading an in-row chunk) of a random row of a table resident in shared
+// memory; the four quarter-warps of a warp read four different rows.  Counts quarter-warp wavefronts per clock.
+__global__ void smem_row_gather(int iters, int rows, float* out) {
+  extern __shared__ float4 sm[];
+  const int NCH = 13;
+  for (int i = threadIdx.x; i < rows * NCH; i += blockDim.x) sm[i] = make_float4(i, 1, 2, 3);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l8 = lane & 7;
+  const int c0 = l8, c1 = (l8 + 8 < NCH) ? l8 + 8 : l8 % NCH;
+  unsigned state = (threadIdx.x >> 3) * 2654435761u + blockIdx.x * 40503u + 12345u;  // one stream per quarter-warp
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < iters; ++r) {
+#pragma unroll 4
+    for (int k = 0; k < 4; ++k) {
+      state = state * 1664525u + 1013904223u;
+      const int row = (int)((state >> 8) % (unsigned)rows);
+      const float4 a = sm[row * NCH + c0], b = sm[row * NCH + c1];
+      acc.x += a.x + b.x; acc.y += a.y + b.y; acc.z += a.z + b.z; acc.w += a.w + b.w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123.456f) out[0] = acc.x;
+}
+
 template <class F>
 float time_ms(F f, int reps = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -110,6 +134,17 @@ int main() {
     double total = (double)sms * 1024 * iters * 8 * 16;
     printf("smem_read     %8.1f GB/s aggregate (%.1f B/clk/SM at %d MHz nominal)\n", total / ms / 1e6,
            total / ms / 1e6 * 1e9 / sms / (prop.clockRate * 1e3), prop.clockRate / 1000);
+  }
+  for (int threads : {800, 1024}) {  // random 208-byte rows per quarter-warp (the message-passing kernel's pattern)
+    const int rows = 612 + 200;  // table + one node tile
+    const size_t smem = (size_t)rows * 13 * 16;
+    CK(cudaFuncSetAttribute(smem_row_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int iters = 4000;
+    float ms = time_ms([&] { smem_row_gather<<<sms, threads, smem>>>(iters, rows, out); });
+    const double wavefronts = (double)sms * (threads / 8) * iters * 4 * 2;  // 2 quarter-warp LDS.128 per row
+    const double clk = ms * 1e-3 * prop.clockRate * 1e3;
+    printf("smem_row_gather %4d threads: %.3f quarter-warp wavefronts/clk/SM (%.1f G rows/s aggregate, %.1f B/clk/SM useful)\n", threads,
+           wavefronts / sms / clk, (double)sms * (threads / 8) * iters * 4 / ms / 1e6, wavefronts / 2 * 208 / sms / clk);
   }
   return 0;
 }
