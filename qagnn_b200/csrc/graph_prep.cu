@@ -22,6 +22,7 @@ struct PrepScratch {
   size_t tmp_src, tmp_tgt;  // [E'] unsorted CSR fill
   size_t inv_src;           // [E'] edge id -> position in the by-source order
   size_t inv_tgt;           // [E'] edge id -> position in the by-target order
+  size_t big_list;          // [2N] work list of (node, direction) segments with more than 32 edges
   size_t total;             // int32 words
 };
 
@@ -41,6 +42,7 @@ PrepScratch make_scratch(int64_t N, int64_t E) {
   s.tmp_tgt = take(Ep);
   s.inv_src = take(Ep);
   s.inv_tgt = take(Ep);
+  s.big_list = take(2 * (size_t)N);
   s.total = o;
   return s;
 }
@@ -157,11 +159,13 @@ __global__ void prep_fill_kernel(const int32_t* __restrict__ src, const int32_t*
   }
 }
 
-// One warp per (node, order): restore ascending edge-id order inside the segment (== stable sort).
+// One warp per (node, order): restore ascending edge-id order inside the segment (== stable sort).  Segments with more
+// than 32 edges (hub nodes) go to a work list that prep_sort_big_segments_kernel sorts one CTA per segment.
 __global__ void prep_sort_segments_kernel(int64_t N, const int32_t* __restrict__ rowptr_src,
                                           const int32_t* __restrict__ rowptr_tgt, const int32_t* __restrict__ tmp_src,
                                           const int32_t* __restrict__ tmp_tgt, int32_t* __restrict__ perm_src,
-                                          int32_t* __restrict__ perm_tgt) {
+                                          int32_t* __restrict__ perm_tgt, int32_t* __restrict__ big_list,
+                                          int32_t* __restrict__ big_count) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -177,13 +181,67 @@ __global__ void prep_sort_segments_kernel(int64_t N, const int32_t* __restrict__
       int rank = 0;
       for (int j = 0; j < deg; ++j) rank += (__shfl_sync(0xffffffffu, id, j) < id);
       if (lane < deg) perm[beg + rank] = id;
-    } else {
-      for (int i = lane; i < deg; i += 32) {
-        const int id = tmp[beg + i];
-        int rank = 0;
-        for (int j = 0; j < deg; ++j) rank += (tmp[beg + j] < id);
-        perm[beg + rank] = id;
+    } else if (lane == 0) {
+      big_list[atomicAdd(big_count, 1)] = (int32_t)w;  // w < 2N < 2^31; the list order does not matter (the result is a sort)
+    }
+  }
+}
+
+// Hub segments: one CTA per segment.  Up to kBigSort edge ids are sorted in shared memory by a bitonic network
+// (O(deg log^2 deg / 512) steps); longer segments fall back to rank counting against shared-memory tiles (O(deg^2 / 512)).
+constexpr int kBigSort = 8192, kBigThreads = 512;
+__global__ void __launch_bounds__(kBigThreads) prep_sort_big_segments_kernel(int64_t N, const int32_t* __restrict__ rowptr_src,
+                                                                             const int32_t* __restrict__ rowptr_tgt,
+                                                                             const int32_t* __restrict__ tmp_src,
+                                                                             const int32_t* __restrict__ tmp_tgt,
+                                                                             int32_t* __restrict__ perm_src, int32_t* __restrict__ perm_tgt,
+                                                                             const int32_t* __restrict__ big_list,
+                                                                             const int32_t* __restrict__ big_count) {
+  __shared__ int32_t buf[kBigSort];
+  const int count = *big_count;
+  for (int item = blockIdx.x; item < count; item += gridDim.x) {
+    const int64_t w = big_list[item];
+    const bool by_tgt = w >= N;
+    const int64_t v = by_tgt ? w - N : w;
+    const int32_t* rowptr = by_tgt ? rowptr_tgt : rowptr_src;
+    const int32_t* tmp = (by_tgt ? tmp_tgt : tmp_src);
+    int32_t* perm = by_tgt ? perm_tgt : perm_src;
+    const int beg = rowptr[v], deg = rowptr[v + 1] - beg;
+    if (deg <= kBigSort) {
+      int n2 = 64;
+      while (n2 < deg) n2 <<= 1;
+      for (int i = threadIdx.x; i < n2; i += kBigThreads) buf[i] = i < deg ? tmp[beg + i] : 0x7fffffff;
+      __syncthreads();
+      for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < n2; i += kBigThreads) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const int32_t a = buf[i], b = buf[ixj];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { buf[i] = b; buf[ixj] = a; }
+            }
+          }
+          __syncthreads();
+        }
       }
+      for (int i = threadIdx.x; i < deg; i += kBigThreads) perm[beg + i] = buf[i];
+      __syncthreads();
+    } else {
+      for (int i0 = 0; i0 < deg; i0 += kBigThreads) {  // every thread ranks one id per round against all tiles
+        const int i = i0 + threadIdx.x;
+        const int32_t id = i < deg ? tmp[beg + i] : 0x7fffffff;
+        int rank = 0;
+        for (int t0 = 0; t0 < deg; t0 += kBigSort) {
+          const int tn = min(kBigSort, deg - t0);
+          __syncthreads();
+          for (int j = threadIdx.x; j < tn; j += kBigThreads) buf[j] = tmp[beg + t0 + j];
+          __syncthreads();
+          for (int j = 0; j < tn; ++j) rank += (buf[j] < id);
+        }
+        if (i < deg) perm[beg + rank] = id;
+      }
+      __syncthreads();
     }
   }
 }
@@ -357,7 +415,13 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
                                                       scr + sc.tmp_tgt);
   QAGNN_CHECK_LAUNCH();
   prep_sort_segments_kernel<<<grid_for(2 * N * 32, 256, 148 * 32), 256, 0, st>>>(
-      N, I(pl.rowptr_src), I(pl.rowptr_tgt), scr + sc.tmp_src, scr + sc.tmp_tgt, I(pl.perm_src), I(pl.perm_tgt));
+      N, I(pl.rowptr_src), I(pl.rowptr_tgt), scr + sc.tmp_src, scr + sc.tmp_tgt, I(pl.perm_src), I(pl.perm_tgt),
+      scr + sc.big_list, I(pl.status) + 1);
+  QAGNN_CHECK_LAUNCH();
+  // hub nodes (more than 32 edges in a segment): one CTA per listed segment; exits at once when the list is empty
+  prep_sort_big_segments_kernel<<<148, kBigThreads, 0, st>>>(N, I(pl.rowptr_src), I(pl.rowptr_tgt), scr + sc.tmp_src,
+                                                             scr + sc.tmp_tgt, I(pl.perm_src), I(pl.perm_tgt),
+                                                             scr + sc.big_list, I(pl.status) + 1);
   QAGNN_CHECK_LAUNCH();
   prep_payload_src_kernel<<<grid_for(Ep, 256), 256, 0, st>>>(Ep, I(pl.perm_src), I(pl.tgt), I(pl.combo),
                                                              I(pl.csr_src_tgt), I(pl.csr_src_combo),

@@ -66,7 +66,10 @@ def edge_table_train(enc, onehot_tab, combo_count, k_calls):
 class _MPCore(torch.autograd.Function):
     """aggr = propagate(...) on node-level projections; forward and backward in libqagnn_b200.so."""
 
+    # under torch.autocast (qagnn.py:91 runs the forward in fp16 autocast when --fp16 is set) the dense layers around this
+    # function may hand it half tensors: the graph part always computes in fp32, like the reference's scatter ops do
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, qkm, ke, me, prep, shape_args, want_alpha):
         lib = _lib.load()
         qkm_c, ke_c, me_c = _lib.f32c(qkm, "qkm"), _lib.f32c(ke, "ke"), _lib.f32c(me, "me")
@@ -90,6 +93,7 @@ class _MPCore(torch.autograd.Function):
         return aggr, None
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, d_aggr, _d_alpha):
         lib = _lib.load()
         qkm, ke, me, alpha_s = ctx.saved_tensors

@@ -507,3 +507,24 @@ def test_decoder_step_graph_matches_module_composition():
         Hh.assert_close(gout, ref_out, f"gnn_out seed {seed}")
         Hh.assert_close(attn, ref_attn, f"pool_attn seed {seed}", atol=2e-5)
         Hh.assert_close(logits, ref_logits, f"logits seed {seed}")
+
+
+@pytest.mark.parametrize("hub_deg", [33, 300, 5000, 9000])
+def test_graph_prep_hub_segments_are_sorted_by_edge_id(hub_deg):
+    """Segments longer than 32 edges go through the per-CTA sort of graph prep (bitonic in shared memory up to 8192 ids,
+    rank counting beyond): perm arrays must still equal the stable sort of the oracle."""
+    N, T, R = 64, 4, 38
+    g = torch.Generator().manual_seed(hub_deg)
+    E = hub_deg * 2 + 200
+    src = torch.randint(0, N, (E,), generator=g)
+    tgt = torch.randint(0, N, (E,), generator=g)
+    idx = torch.randperm(E, generator=g)
+    src[idx[:hub_deg]] = 5            # node 5: a source hub
+    tgt[idx[hub_deg:2 * hub_deg]] = 9  # node 9: a target hub
+    ei = torch.stack([src, tgt])
+    et = torch.randint(0, R, (E,), generator=g)
+    nt = torch.randint(0, T, (N,), generator=g)
+    prep = GraphPrep(ei.to(DEV), et.to(DEV), nt.to(DEV), T, R, 0)
+    ref = O.graph_prep_oracle(ei, et, nt, T, R)
+    for key in ("rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt"):
+        assert np.array_equal(prep.array(key).cpu().numpy().astype(np.int64), ref[key]), key

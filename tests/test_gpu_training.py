@@ -158,3 +158,68 @@ def test_whole_decoder_training_step_matches_reference():
             continue
         assert got[pname].grad is not None, pname
         _grad_close(got[pname].grad, ref_g, f"dL/d{pname}", floor=1e-2 * gmax)
+
+
+def test_training_step_under_fp16_autocast_and_grad_scaler():
+    """qagnn.py:91,249-278 with --fp16: forward under autocast, scaled backward, optimiser step.  The CUDA message passing keeps
+    fp32 inside (custom_fwd cast), the dense layers run in half: finite loss / gradients, output close to the fp32 forward."""
+    fx = Hh.load_golden("train_cfg1_peaky_k2")
+    inp, sd = Hh.regen_mp_inputs(fx)
+    mod = _module(fx, sd).train()
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    args = (d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    ref = mod(*args).detach()
+    opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
+    scaler = torch.amp.GradScaler("cuda")
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = mod(*args)
+        loss = out.float().square().mean()
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    assert torch.isfinite(loss) and all(p.grad is None or torch.isfinite(p.grad).all() for p in mod.parameters())
+    assert float((out.float() - ref).abs().max()) < 5e-2 * max(1.0, float(ref.abs().max()))
+
+
+def test_lm_qagnn_training_step_runs_end_to_end():
+    """The whole LM_QAGNN (tiny random-init RoBERTa + decoder) in .train(): cross-entropy over the choices, backward, one
+    optimiser step — the loop body of qagnn.py:249-278 with this package's classes."""
+    from transformers import RobertaConfig
+    torch.manual_seed(0)
+    cfg = RobertaConfig(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                        max_position_embeddings=40)
+    bs, nc, n, D, k = 2, 5, 20, 64, 2
+    model = qagnn_b200.LM_QAGNN(None, "roberta-large", k, 4, 38, n_concept=50, concept_dim=D, concept_in_dim=32, n_attention_head=2,
+                                fc_dim=D, n_fc_layer=0, p_emb=0.1, p_gnn=0.1, p_fc=0.1, init_range=0.02,
+                                encoder_config={"config": cfg}).to(DEV).train()
+    from oracle import qagnn_oracle as O
+    g = torch.Generator().manual_seed(1)
+    inp = O.synth_graph_batch(bs * nc, n, 40, D, 38, seed=2, realistic=True)
+    ei, et = [], []
+    for q in range(bs):
+        ei.append([]); et.append([])
+        for c in range(nc):
+            gi = q * nc + c
+            sel = (inp["edge_index"][0] >= gi * n) & (inp["edge_index"][0] < (gi + 1) * n)
+            ei[-1].append((inp["edge_index"][:, sel] - gi * n).to(DEV)); et[-1].append(inp["edge_type"][sel].to(DEV))
+    lm = [torch.randint(3, 90, (bs, nc, 12), generator=g).to(DEV), torch.ones(bs, nc, 12, dtype=torch.long, device=DEV),
+          torch.zeros(bs, nc, 12, dtype=torch.long, device=DEV), torch.zeros(bs, nc, 12, dtype=torch.long, device=DEV)]
+    concept_ids = torch.randint(1, 51, (bs, nc, n), generator=g)
+    concept_ids[..., 0] = 0
+    dec = [concept_ids.to(DEV), inp["node_type"].view(bs, nc, n).to(DEV), inp["node_score"].view(bs, nc, n, 1).to(DEV),
+           inp["adj_lengths"].view(bs, nc).to(DEV)]
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    labels = torch.tensor([1, 3], device=DEV)
+    before = model.decoder.gnn.gnn_layers[0].linear_key.weight.detach().clone()
+    logits, _ = model(*lm, *dec, ei, et)
+    assert logits.shape == (bs, nc) and logits.requires_grad
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    opt.step()
+    assert torch.isfinite(loss)
+    assert model.decoder.gnn.gnn_layers[0].linear_key.weight.grad is not None
+    assert not torch.equal(before, model.decoder.gnn.gnn_layers[0].linear_key.weight.detach())
+    with torch.no_grad():  # and the eval path sees the updated weights
+        model.eval()
+        logits_eval, _ = model(*lm, *dec, ei, et)
+    assert torch.isfinite(logits_eval).all()
