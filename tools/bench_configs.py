@@ -127,6 +127,41 @@ def cfg5(path="auto"):
             "stages_ms": {k_: v[0] / max(v[1], 1) for k_, v in prof.items() if v[1]}}
 
 
+def train():
+    """Training step of QAGNN_Message_Passing at cfg2 (forward with batch statistics + dropout, backward through the CUDA
+    message-passing kernels, SGD step): wall time per step and the share of the hand-written kernels."""
+    B, n, e, D, k = 320, 200, 1000, 200, 5
+    inp = O.synth_graph_batch(B, n, e, D, 38, 100)
+    sd = O.random_state_dict(k, D, 4, 38, "prod", 0)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D, dropout=0.2)
+    mod.load_state_dict(sd)
+    mod = mod.to(dev).train()
+    d = {k_: v.to(dev) for k_, v in inp.items()}
+    opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
+    prep = mod.prepare_graph(d["edge_index"], d["edge_type"], d["node_type"].view(-1))
+    prep.n_per_graph = 0
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"], prep=prep)
+        out.square().mean().backward()
+        opt.step()
+    ms = gpu_time(step, 10, warm=3)
+    from qagnn_b200 import _lib
+    lib = _lib.load()
+    lib.qagnn_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    lib.qagnn_profile_enable(0)
+    mod.eval()
+    with torch.no_grad():
+        ms_eval = gpu_time(lambda: mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"]), 20)
+    return {"config": "train: cfg2 batch, one optimiser step of QAGNN_Message_Passing (k=5), fp32", "ms_per_train_step": ms,
+            "ms_per_eval_forward_per_kernel_launches": ms_eval, "edge_layers_per_s_training": k * B * e / (ms * 1e-3),
+            "cuda_mp_forward_ms_per_step": prof["message_passing"][0]}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg5"]
     for name in which:
