@@ -225,6 +225,9 @@ def synth_step_inputs(rank):
     inp["sent_vecs"] = torch.randn(B, SENT_DIM, generator=g) * 0.5
     if "adj_lengths" not in inp or inp["adj_lengths"] is None:
         inp["adj_lengths"] = torch.full((B,), n, dtype=torch.long)
+    # the batch is packed graph by graph, as LM_QAGNN.batch_graph / qagnn_b200.data.PackedAdjBatchGenerator deliver it
+    cnt = torch.bincount(inp["edge_index"][0] // n, minlength=B)
+    inp["graph_ptr"] = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt, 0)])
     return inp
 
 
@@ -260,7 +263,8 @@ def run_b200_arm(args):
     pooler, fc = build_decoder_tail(D, SENT_DIM, dev)
     N, E = B * n, inp["edge_index"].size(1)
 
-    host = {k_: inp[k_].pin_memory() for k_ in DecoderStep.FIELDS}
+    host = {k_: inp[k_].pin_memory() for k_ in DecoderStep.PACKED_FIELDS}
+    max_edges = int((inp["graph_ptr"][1:] - inp["graph_ptr"][:-1]).max())
     d = {k_: v.to(dev, non_blocking=True) for k_, v in host.items()}
     torch.cuda.synchronize()
 
@@ -279,11 +283,11 @@ def run_b200_arm(args):
     # and the answer MLP — replayed as ONE CUDA graph on static device buffers
     group = dist.group.WORLD if world > 1 else None
     try:
-        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=not args.no_cuda_graph)
+        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=not args.no_cuda_graph, max_edges=max_edges)
     except Exception as exc:  # noqa: BLE001  capture unavailable (e.g. a NCCL build that cannot be captured): per-kernel launches
         if args.no_cuda_graph:
             raise
-        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False)
+        step = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False, max_edges=max_edges)
         step.mode = f"per-kernel launches (CUDA graph capture failed: {type(exc).__name__})"
     launch_mode = step.mode if step.graph is not None or args.no_cuda_graph else step.mode
 
@@ -296,8 +300,8 @@ def run_b200_arm(args):
             refs = []
             for r in range(world):
                 ri = synth_step_inputs(r)
-                rd = {k_: ri[k_].to(dev) for k_ in DecoderStep.FIELDS}
-                refs.append(DecoderStep(mod, pooler, fc, rd, 1, None, use_cuda_graph=False).run()[0])
+                rd = {k_: ri[k_].to(dev) for k_ in DecoderStep.PACKED_FIELDS}
+                refs.append(DecoderStep(mod, pooler, fc, rd, 1, None, use_cuda_graph=False, max_edges=max_edges).run()[0])
             ref = torch.cat(refs)
             logits_err = (got - ref).abs().max().item()
             if logits_err > 1e-5 + 1e-5 * ref.abs().max().item():
@@ -310,8 +314,8 @@ def run_b200_arm(args):
     # inputs from pinned host memory and downloads the step's results (logits of the whole job + this rank's pooling
     # attention); copies run on their own streams, double-buffered (one captured graph per buffer set)
     def make_step(dev_inputs):
-        return DecoderStep(mod, pooler, fc, dev_inputs, world, group, use_cuda_graph=step.graph is not None)
-    runner = StreamedRunner(mod, host, dev, depth=2, make_step=make_step, fields=DecoderStep.FIELDS, download=(0, 1))
+        return DecoderStep(mod, pooler, fc, dev_inputs, world, group, use_cuda_graph=step.graph is not None, max_edges=max_edges)
+    runner = StreamedRunner(mod, host, dev, depth=2, make_step=make_step, fields=DecoderStep.PACKED_FIELDS, download=(0, 1))
     # second e2e figure, round 1's definition: bare QAGNN_Message_Passing.forward, [B,n,D] node output downloaded
     mod.use_cuda_graph = not args.no_cuda_graph
     runner_nodes = StreamedRunner(mod, host, dev, depth=2)
@@ -372,7 +376,7 @@ def run_b200_arm(args):
     # kernel-level pass: the same K steps launched kernel by kernel with the library's CUDA-event stage timers on the
     # launching stream (events cannot be timed inside a replayed graph); feeds `roofline`, `stages`, `gpu_launches`
     mod.use_cuda_graph = False
-    eager = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False)
+    eager = DecoderStep(mod, pooler, fc, d, world, group, use_cuda_graph=False, max_edges=max_edges)
     eager.run()
     ms_eager, launches, prof = timed(eager.run, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
@@ -419,14 +423,14 @@ def run_b200_arm(args):
                    "shards; ONE NCCL all_gather_into_tensor of the pooled features [B, 2D+sent_dim] per step, inside the step's "
                    "CUDA graph, then the answer MLP on the whole job's batch)" if world > 1 else "single GPU",
                    "l2": f"no flush: a step streams the {lib.qagnn_forward_workspace_bytes(_lib.C.byref(mod._shape(N, E, n))) / 1e6:.0f} MB "
-                         "workspace + 51 MB inputs, > 126 MB L2", "step": "graph prep + 5 x (projection, message passing, "
+                         "workspace + 51 MB inputs, > 126 MB L2", "step": "graph prep (packed batch: one launch) + 5 x (projection, message passing, "
                    "node MLP) + Vh/Vx epilogue + attention pooling + (all-gather) + answer MLP, inputs resident in HBM",
                    "launch": launch_mode, "numa_node_bound": numa},
         "qa_pairs_per_s": world * B / (ms_step * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes(), "d2h_bytes_per_step": runner.d2h_bytes(),
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "qagnn_b200.pipeline.StreamedRunner around qagnn_b200.pipeline.DecoderStep: per step H2D of H/edge_index/"
-                       "edge_type/node_type/node_score/sent_vecs/adj_lengths from pinned host memory, the step, D2H of its results "
+                       "edge_type/node_type/node_score/sent_vecs/adj_lengths/graph_ptr from pinned host memory, the step, D2H of its results "
                        "(logits of the whole job + pooling attention) into pinned memory; copies on separate streams, "
                        "double-buffered, so they overlap the neighbouring steps' kernels"},
         "gpu_launches": int(launches),

@@ -142,6 +142,15 @@ int32_t qagnn_graph_prep(const int64_t *edge_index, const int64_t *edge_type, co
                          const qagnn_shape *shape, void *prep, size_t prep_bytes, int32_t validate,
                          void *stream);
 
+/* The same prep for a PACKED batch: the edges of sub-graph g occupy [graph_ptr[g], graph_ptr[g+1]) of edge_index / edge_type (what
+ * LM_QAGNN.batch_graph, modeling_qagnn.py:244-251, and qagnn_b200.data.pack_adj produce; graph_ptr int64 [N/n_per_graph + 1] on the
+ * DEVICE) and max_edges_per_graph bounds their length (host value).  One CTA builds everything for one sub-graph in shared memory:
+ * one launch instead of twelve, bit-identical arrays.  QAGNN_ERR_UNSUPPORTED when a sub-graph does not fit one CTA's shared
+ * memory (use qagnn_graph_prep); an edge outside its sub-graph's node range sets the same status bit as qagnn_graph_prep. */
+int32_t qagnn_graph_prep_packed(const int64_t *edge_index, const int64_t *edge_type, const int64_t *node_type,
+                                const int64_t *graph_ptr, int32_t max_edges_per_graph, const qagnn_shape *shape, void *prep,
+                                size_t prep_bytes, int32_t validate, void *stream);
+
 /* ---- weight folding (once per set of weights) --------------------------------------------- */
 
 size_t qagnn_fold_bytes(const qagnn_shape *shape);

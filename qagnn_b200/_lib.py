@@ -52,6 +52,7 @@ EXPORTS = {
     "qagnn_graph_prep_layout": (C.c_int32, [C.c_int64, C.c_int64, C.POINTER(PrepLayout)]),
     "qagnn_graph_prep_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "qagnn_graph_prep": (C.c_int32, [_P, _P, _P, C.POINTER(Shape), _P, C.c_size_t, C.c_int32, _P]),
+    "qagnn_graph_prep_packed": (C.c_int32, [_P, _P, _P, _P, C.c_int32, C.POINTER(Shape), _P, C.c_size_t, C.c_int32, _P]),
     "qagnn_fold_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "qagnn_fold_weights": (C.c_int32, [C.POINTER(Shape), C.POINTER(EdgeEncoderParams), C.POINTER(LayerParams),
                                        C.POINTER(MPParams), _P, C.c_size_t, _P]),

@@ -323,6 +323,180 @@ __global__ void __launch_bounds__(256) prep_degree_order_kernel(int npg, const i
   }
 }
 
+// ---- packed batches: one CTA builds the whole prep of ONE sub-graph in shared memory ------------------------------------
+// When the caller knows where each sub-graph's edges start (graph_ptr: the batch generator / pack_adj / batch_graph lay
+// the edges out graph by graph), everything above — count, scan, fill, in-segment sort, payloads, degree order — is local
+// to a sub-graph: ~1200 edges and 200 nodes at cfg2.  One launch instead of twelve; the result is bit-identical to the
+// general pipeline (tests/test_gpu_parity.py) because every array is a function of the stable edge-id order only.
+// Local edge index i: real edges i < e_g (edge id gp[g] + i), then the self loop of local node i - e_g (edge id E + g*n + ...).
+struct PackedPrepArgs {
+  const int64_t *edge_index, *edge_type, *node_type, *graph_ptr;
+  int64_t N, E;
+  int T, R, npg, cap;
+  int32_t *src, *tgt, *combo, *rowptr_src, *rowptr_tgt, *perm_src, *perm_tgt, *csr_src_tgt, *csr_src_combo, *csr_tgt_src,
+      *csr_tgt_combo, *csr_tgt_apos, *pk_src, *pk_tgt, *csr_src_tpos, *order_src, *order_tgt, *status;
+  uint2 *ninfo_src, *ninfo_tgt;
+};
+
+constexpr int kPackedThreads = 256;
+
+__global__ void __launch_bounds__(kPackedThreads) prep_packed_graph_kernel(const PackedPrepArgs a) {
+  extern __shared__ int32_t sm_pp[];
+  const int n = a.npg, cap = a.cap, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kPackedThreads / 32;
+  int32_t* ntype = sm_pp;             // [n]
+  int32_t* cnt_s = ntype + n;         // [n + 1]  counts, then exclusive local row pointers
+  int32_t* cnt_t = cnt_s + n + 1;     // [n + 1]
+  int32_t* cur_s = cnt_t + n + 1;     // [n]      fill cursors, later histogram scratch
+  int32_t* cur_t = cur_s + n;         // [n]
+  int32_t* lsrc = cur_t + n;          // [cap]    local source of local edge i
+  int32_t* ltgt = lsrc + cap;         // [cap]
+  int32_t* lcombo = ltgt + cap;       // [cap]
+  int32_t* tmp_s = lcombo + cap;      // [cap]    unsorted CSR fill (local edge indices)
+  int32_t* tmp_t = tmp_s + cap;       // [cap]
+  int32_t* perm_s = tmp_t + cap;      // [cap]    sorted
+  int32_t* perm_t = perm_s + cap;     // [cap]
+  int32_t* inv_s = perm_t + cap;      // [cap]    local edge -> position
+  int32_t* inv_t = inv_s + cap;       // [cap]
+  __shared__ int hist[256], hbase[256];
+
+  const int64_t g = blockIdx.x;
+  const int64_t e0 = a.graph_ptr[g], e1 = a.graph_ptr[g + 1];
+  const int eg = (int)(e1 - e0), ep = eg + n;  // real edges, edges incl. self loops (ep <= cap, checked on the host)
+  const int64_t v0 = g * n;
+  const int64_t base = e0 + v0;  // entries of the CSR orders that belong to earlier sub-graphs
+  if (e0 < 0 || e1 < e0 || e1 > a.E || ep > cap) {  // graph_ptr disagrees with E / max_edges_per_graph: nothing is touched
+    if (tid == 0) atomicOr(a.status, 16);
+    return;
+  }
+  int bad = 0;
+  for (int i = tid; i < n; i += kPackedThreads) {
+    int64_t t = a.node_type[v0 + i];
+    if (t < 0 || t >= a.T) { bad |= 4; t = min(max(t, (int64_t)0), (int64_t)a.T - 1); }
+    ntype[i] = (int32_t)t;
+    cnt_s[i] = 0; cnt_t[i] = 0; cur_s[i] = 0; cur_t[i] = 0;
+  }
+  if (tid == 0) { cnt_s[n] = 0; cnt_t[n] = 0; }
+  __syncthreads();
+  // edges -> local ids, combo, counts; global src / tgt / combo in edge-id order
+  for (int i = tid; i < ep; i += kPackedThreads) {
+    int sl, tl, r;
+    int64_t gid;
+    if (i < eg) {
+      gid = e0 + i;
+      int64_t s = a.edge_index[gid], t = a.edge_index[a.E + gid], rr = a.edge_type[gid];
+      if (s < 0 || s >= a.N || t < 0 || t >= a.N) { bad |= 1; s = min(max(s, (int64_t)0), a.N - 1); t = min(max(t, (int64_t)0), a.N - 1); }
+      if (rr < 0 || rr >= a.R) { bad |= 2; rr = min(max(rr, (int64_t)0), (int64_t)a.R - 1); }
+      if (s / n != g || t / n != g) bad |= 8;  // not an edge of this sub-graph
+      sl = (int)min(max(s - v0, (int64_t)0), (int64_t)n - 1);
+      tl = (int)min(max(t - v0, (int64_t)0), (int64_t)n - 1);
+      r = (int)rr;
+      a.src[gid] = (int32_t)s; a.tgt[gid] = (int32_t)t;
+    } else {
+      sl = tl = i - eg;
+      r = a.R;
+      gid = a.E + v0 + sl;
+      a.src[gid] = (int32_t)(v0 + sl); a.tgt[gid] = (int32_t)(v0 + sl);
+    }
+    const int c = i < eg ? (r * a.T + ntype[sl]) * a.T + ntype[tl] : a.R * a.T * a.T + ntype[sl];
+    a.combo[gid] = c;
+    lsrc[i] = sl; ltgt[i] = tl; lcombo[i] = c;
+    atomicAdd(&cnt_s[sl], 1);
+    atomicAdd(&cnt_t[tl], 1);
+  }
+  if (bad) atomicOr(a.status, bad);
+  __syncthreads();
+  // exclusive scan of both count arrays (warp 0: by source, warp 1: by target), n <= 65535
+  if (warp < 2) {
+    int32_t* cnt = warp == 0 ? cnt_s : cnt_t;
+    const int chunk = (n + 31) / 32, b0 = lane * chunk, b1 = min(n, b0 + chunk);
+    int sum = 0;
+    for (int i = b0; i < b1; ++i) sum += cnt[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    int run = incl - sum;
+    for (int i = b0; i < b1; ++i) { const int c = cnt[i]; cnt[i] = run; run += c; }
+    if (lane == 31) cnt[n] = incl;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kPackedThreads) {
+    a.rowptr_src[v0 + i] = (int32_t)(base + cnt_s[i]);
+    a.rowptr_tgt[v0 + i] = (int32_t)(base + cnt_t[i]);
+  }
+  if (g == gridDim.x - 1 && tid == 0) { a.rowptr_src[a.N] = (int32_t)(a.E + a.N); a.rowptr_tgt[a.N] = (int32_t)(a.E + a.N); }
+  // unordered fill, then ascending edge order inside every segment (== stable sort by node)
+  for (int i = tid; i < ep; i += kPackedThreads) {
+    tmp_s[cnt_s[lsrc[i]] + atomicAdd(&cur_s[lsrc[i]], 1)] = i;
+    tmp_t[cnt_t[ltgt[i]] + atomicAdd(&cur_t[ltgt[i]], 1)] = i;
+  }
+  __syncthreads();
+  for (int w = warp; w < 2 * n; w += nwarps) {  // one warp per (node, direction); lanes over the segment's positions
+    const bool by_t = w >= n;
+    const int v = by_t ? w - n : w;
+    const int32_t* cnt = by_t ? cnt_t : cnt_s;
+    const int32_t* tmp = by_t ? tmp_t : tmp_s;
+    int32_t* perm = by_t ? perm_t : perm_s;
+    int32_t* inv = by_t ? inv_t : inv_s;
+    const int b = cnt[v], deg = cnt[v + 1] - b;
+    for (int q = lane; q < deg; q += 32) {
+      const int id = tmp[b + q];
+      int rank = 0;
+      for (int j = 0; j < deg; ++j) rank += (tmp[b + j] < id);
+      perm[b + rank] = id;
+      inv[id] = b + rank;
+    }
+  }
+  __syncthreads();
+  // payloads in both orders
+  for (int p = tid; p < ep; p += kPackedThreads) {
+    {
+      const int i = perm_s[p];
+      const int64_t gid = i < eg ? e0 + i : a.E + v0 + (i - eg);
+      const int tl = ltgt[i], c = lcombo[i];
+      a.perm_src[base + p] = (int32_t)gid;
+      a.csr_src_tgt[base + p] = (int32_t)(v0 + tl);
+      a.csr_src_combo[base + p] = c;
+      a.pk_src[base + p] = (int32_t)(((uint32_t)tl << 16) | ((uint32_t)c & 0xffffu));
+      a.csr_src_tpos[base + p] = (int32_t)(base + inv_t[i]);
+    }
+    {
+      const int i = perm_t[p];
+      const int64_t gid = i < eg ? e0 + i : a.E + v0 + (i - eg);
+      const int sl = lsrc[i], c = lcombo[i];
+      a.perm_tgt[base + p] = (int32_t)gid;
+      a.csr_tgt_src[base + p] = (int32_t)(v0 + sl);
+      a.csr_tgt_combo[base + p] = c;
+      a.csr_tgt_apos[base + p] = (int32_t)(base + inv_s[i]);
+      a.pk_tgt[base + p] = (int32_t)(((uint32_t)sl << 16) | ((uint32_t)c & 0xffffu));
+    }
+  }
+  // degree-sorted schedule of the tiled kernel, both directions (see prep_degree_order_kernel)
+  for (int dir = 0; dir < 2; ++dir) {
+    const int32_t* cnt = dir ? cnt_t : cnt_s;
+    int32_t* order = (dir ? a.order_tgt : a.order_src) + v0;
+    uint2* ninfo = (dir ? a.ninfo_tgt : a.ninfo_src) + v0;
+    __syncthreads();
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kPackedThreads) atomicAdd(&hist[min(cnt[i + 1] - cnt[i], 255)], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int b = 255; b >= 0; --b) { hbase[b] = run; run += hist[b]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kPackedThreads) {
+      const int deg = cnt[i + 1] - cnt[i];
+      const int slot = atomicAdd(&hbase[min(deg, 255)], 1);
+      order[slot] = i;
+      ninfo[slot] = make_uint2((uint32_t)i | ((uint32_t)min(deg, 0xffff) << 16), (uint32_t)(base + cnt[i]));
+    }
+  }
+}
+
 inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -440,6 +614,54 @@ extern "C" int32_t qagnn_graph_prep(const int64_t* edge_index, const int64_t* ed
                                                                           (uint2*)I(pl.ninfo_src), (uint2*)I(pl.ninfo_tgt));
     QAGNN_CHECK_LAUNCH();
   }
+  if (validate) {
+    int32_t h = 0;
+    QAGNN_CHECK_CUDA(cudaMemcpyAsync(&h, I(pl.status), 4, cudaMemcpyDeviceToHost, st));
+    QAGNN_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (h != 0) return QAGNN_ERR_INDEX_RANGE;
+  }
+  return QAGNN_OK;
+}
+
+extern "C" int32_t qagnn_graph_prep_packed(const int64_t* edge_index, const int64_t* edge_type, const int64_t* node_type,
+                                           const int64_t* graph_ptr, int32_t max_edges_per_graph, const qagnn_shape* shape,
+                                           void* prep, size_t prep_bytes, int32_t validate, void* stream) {
+  if (!shape || !node_type || !prep || !graph_ptr) return QAGNN_ERR_INVALID_ARGUMENT;
+  const int64_t N = shape->N, E = shape->E;
+  if (E > 0 && (!edge_index || !edge_type)) return QAGNN_ERR_INVALID_ARGUMENT;
+  if (shape->T <= 0 || shape->R <= 0 || max_edges_per_graph < 0) return QAGNN_ERR_INVALID_ARGUMENT;
+  const int npg = shape->n_per_graph;
+  const int64_t Ccombo = (int64_t)shape->R * shape->T * shape->T + shape->T;
+  if (npg <= 0 || npg > 65535 || N % npg != 0 || Ccombo > 65536) return QAGNN_ERR_UNSUPPORTED;
+  qagnn_prep_layout pl;
+  QAGNN_RETURN_IF(qagnn_graph_prep_layout(N, E, &pl));
+  if (prep_bytes < pl.total_bytes) return QAGNN_ERR_WORKSPACE;
+  const int cap = max_edges_per_graph + npg;
+  const size_t smem = ((size_t)5 * npg + 2 + (size_t)9 * cap) * sizeof(int32_t);
+  static int smem_c[kMaxDevices] = {0};
+  static size_t attr[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (smem_c[dev] == 0) cudaDeviceGetAttribute(&smem_c[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem + 4096 > (size_t)smem_c[dev]) return QAGNN_ERR_UNSUPPORTED;  // sub-graphs too large for one CTA: use qagnn_graph_prep
+  if (smem + 4096 > 48 * 1024 && smem > attr[dev]) {  // the kernel also has 2 KB of static shared memory
+    QAGNN_CHECK_CUDA(cudaFuncSetAttribute(prep_packed_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[dev] = smem;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)prep;
+  auto I = [&](size_t off) { return (int32_t*)(base + off); };
+  ProfScope ps(QAGNN_PROF_GRAPH_PREP, st);
+  QAGNN_CHECK_CUDA(cudaMemsetAsync(I(pl.status), 0, 16, st));
+  PackedPrepArgs a;
+  a.edge_index = edge_index; a.edge_type = edge_type; a.node_type = node_type; a.graph_ptr = graph_ptr;
+  a.N = N; a.E = E; a.T = shape->T; a.R = shape->R; a.npg = npg; a.cap = cap;
+  a.src = I(pl.src); a.tgt = I(pl.tgt); a.combo = I(pl.combo); a.rowptr_src = I(pl.rowptr_src); a.rowptr_tgt = I(pl.rowptr_tgt);
+  a.perm_src = I(pl.perm_src); a.perm_tgt = I(pl.perm_tgt); a.csr_src_tgt = I(pl.csr_src_tgt); a.csr_src_combo = I(pl.csr_src_combo);
+  a.csr_tgt_src = I(pl.csr_tgt_src); a.csr_tgt_combo = I(pl.csr_tgt_combo); a.csr_tgt_apos = I(pl.csr_tgt_apos);
+  a.pk_src = I(pl.pk_src); a.pk_tgt = I(pl.pk_tgt); a.csr_src_tpos = I(pl.csr_src_tpos); a.order_src = I(pl.order_src);
+  a.order_tgt = I(pl.order_tgt); a.status = I(pl.status); a.ninfo_src = (uint2*)I(pl.ninfo_src); a.ninfo_tgt = (uint2*)I(pl.ninfo_tgt);
+  prep_packed_graph_kernel<<<(unsigned)(N / npg), kPackedThreads, smem, st>>>(a);
+  QAGNN_CHECK_LAUNCH();
   if (validate) {
     int32_t h = 0;
     QAGNN_CHECK_CUDA(cudaMemcpyAsync(&h, I(pl.status), 4, cudaMemcpyDeviceToHost, st));

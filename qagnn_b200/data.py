@@ -25,16 +25,31 @@ class PackedAdj:
     n_nodes: int
     buf: torch.Tensor = None
 
+    graph_ptr_dev: torch.Tensor = None   # graph_ptr on the device of edge_index (packed graph prep, one launch per batch)
+    max_edges: int = -1                  # max edges of one sub-graph (host value; -1 = derive from graph_ptr)
+
     def to(self, device, non_blocking=True):
+        gp = self.graph_ptr
+        if torch.cuda.is_available() and torch.device(device).type == "cuda" and not gp.is_cuda and not gp.is_pinned():
+            gp = gp.pin_memory()
+        gpd = gp.to(device, non_blocking=non_blocking)
+        me = self.max_edges if self.max_edges >= 0 else (int((self.graph_ptr[1:] - self.graph_ptr[:-1]).max()) if self.graph_ptr.numel() > 1 else 0)
         if self.buf is not None:
             b = self.buf.to(device, non_blocking=non_blocking)
-            return PackedAdj(b[:2], b[2], self.graph_ptr, self.n_nodes, b)
+            return PackedAdj(b[:2], b[2], self.graph_ptr, self.n_nodes, b, gpd, me)
         return PackedAdj(self.edge_index.to(device, non_blocking=non_blocking),
-                         self.edge_type.to(device, non_blocking=non_blocking), self.graph_ptr, self.n_nodes)
+                         self.edge_type.to(device, non_blocking=non_blocking), self.graph_ptr, self.n_nodes, None, gpd, me)
 
-    # LM_QAGNN.forward slices inputs positionally and calls .size() only on tensors before the last two
+    # LM_QAGNN.forward slices inputs positionally and calls .size() only on tensors before the last two; everywhere an
+    # (edge_index, edge_type) pair is expected a PackedAdj unpacks / indexes as that pair
     def __iter__(self):
         return iter((self.edge_index, self.edge_type))
+
+    def __getitem__(self, i):
+        return (self.edge_index, self.edge_type)[i]
+
+    def __len__(self):
+        return 2
 
 
 def pack_adj(edge_index_nested, edge_type_nested, n_nodes, pin=True):

@@ -66,7 +66,9 @@ class GraphPrep:
     """Owns the opaque graph-prep workspace of one batched graph (qagnn_graph_prep)."""
 
     def __init__(self, edge_index, edge_type, node_type, n_ntype, n_etype, n_per_graph=0, validate=True,
-                 allow_general_fallback=False):
+                 allow_general_fallback=False, graph_ptr=None, max_edges=-1):
+        """graph_ptr (device int64 [n_graphs + 1]) + max_edges (host int): the batch is PACKED graph by graph — the whole
+        prep is then one kernel launch (qagnn_graph_prep_packed) instead of twelve."""
         lib = _lib.load()
         ei = _lib.i64c(edge_index, "edge_index")
         et = _lib.i64c(edge_type, "edge_type")
@@ -81,20 +83,33 @@ class GraphPrep:
         self.buf = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=self.device)
         self._combo_order = None
 
+        packed = graph_ptr is not None and max_edges >= 0 and self.n_per_graph > 0
+        if packed:
+            gp = _lib.i64c(graph_ptr, "graph_ptr")
+            if gp.numel() != self.N // max(self.n_per_graph, 1) + 1:
+                raise ValueError("graph_ptr must have one entry per sub-graph plus one")
+
         def run():
             shape = _lib.Shape(self.N, self.E, 4, 1, n_ntype, n_etype, 0, self.n_per_graph)
             with torch.cuda.device(self.device):
+                if packed and self.n_per_graph > 0:
+                    st_ = lib.qagnn_graph_prep_packed(_lib.ptr(ei) if self.E else None, _lib.ptr(et) if self.E else None, _lib.ptr(nt),
+                                                      _lib.ptr(gp), int(max_edges), C.byref(shape), _lib.ptr(self.buf), self.buf.numel(),
+                                                      int(bool(validate)), _lib.stream_ptr(self.device))
+                    if st_ != -5:  # QAGNN_ERR_UNSUPPORTED: sub-graphs too large for one CTA -> the general pipeline below
+                        return st_
                 return lib.qagnn_graph_prep(_lib.ptr(ei) if self.E else None, _lib.ptr(et) if self.E else None, _lib.ptr(nt),
                                             C.byref(shape), _lib.ptr(self.buf), self.buf.numel(), int(bool(validate)),
                                             _lib.stream_ptr(self.device))
         st = run()
         if st == -3 and self.n_per_graph > 0 and allow_general_fallback and int(self.array("status")[0].item()) == 8:
+            packed = False
             # the only complaint is an edge that crosses a sub-graph boundary: n_per_graph is a layout HINT for the
             # shared-memory-tiled kernels, the reference accepts any batched edge_index -> use the general CSR kernels
             self.n_per_graph = 0
             st = run()
         _lib.check(st, "qagnn_graph_prep")
-        self._keep = (ei, et, nt)
+        self._keep = (ei, et, nt, graph_ptr)
 
     def combo_order(self):
         """int32 [E+N]: by-source edge positions stably sorted by combo (for the backward's edge-table gradient)."""
@@ -334,6 +349,12 @@ class QAGNN_Message_Passing(nn.Module):
                              f"of range or crossing a sub-graph boundary (status bits {int(host.item())}); its output was "
                              "computed from clamped indices")
 
+    def check_batch(self, A, node_type):
+        """Validates the indices of a batch once (synchronising); raises IndexError like forward() with check_indices."""
+        n = node_type.size(1) if node_type.dim() == 2 else 0
+        GraphPrep(A[0], A[1], node_type.reshape(-1), self.n_ntype, self.n_etype, n, True, allow_general_fallback=True,
+                  graph_ptr=getattr(A, "graph_ptr_dev", None), max_edges=getattr(A, "max_edges", -1))
+
     def prepare_graph(self, edge_index, edge_type, node_type):
         """Builds the layer-invariant graph workspace; pass it back via forward(..., prep=) to amortise
         it over repeated forwards on the same batch."""
@@ -388,10 +409,13 @@ class QAGNN_Message_Passing(nn.Module):
         sc = _lib.f32c(node_score.reshape(-1), "node_score")
         if nt.numel() != B * n or sc.numel() != B * n:
             raise ValueError("node_type / node_score must be [batch, n_node(, 1)]")
-        edge_index, edge_type = A
+        edge_index, edge_type = A  # a (edge_index, edge_type) pair, or a qagnn_b200.data.PackedAdj (iterates as that pair)
         if prep is None:
+            gp, me = getattr(A, "graph_ptr_dev", None), getattr(A, "max_edges", -1)
+            if gp is not None and getattr(A, "n_nodes", n) != n:
+                gp = None  # packed for another node count: its graph_ptr still holds, its offsets do not -> general prep
             prep = GraphPrep(edge_index, edge_type, nt, self.n_ntype, self.n_etype, n, self.check_indices,
-                             allow_general_fallback=True)
+                             allow_general_fallback=True, graph_ptr=gp, max_edges=me)
         self._last_prep = prep
         if prep.N != B * n:
             raise ValueError("graph workspace was built for a different number of nodes")
@@ -413,6 +437,8 @@ class QAGNN_Message_Passing(nn.Module):
 def _mp_forward_graphed(self, H, A, node_type, node_score):
     """CUDA-graph replay of forward() for inputs that live in the same device buffers as when it was captured."""
     tensors = [H, A[0], A[1], node_type, node_score]
+    if getattr(A, "graph_ptr_dev", None) is not None:
+        tensors.append(A.graph_ptr_dev)
     key = (tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors),
            _version_key(list(self.parameters()) + list(self.buffers())))
     entry = self._graphs.get(key)
@@ -421,8 +447,7 @@ def _mp_forward_graphed(self, H, A, node_type, node_score):
         check, self.check_indices = self.check_indices, False
         try:
             if check:  # validate once, eagerly, before trusting the capture
-                GraphPrep(A[0], A[1], node_type, self.n_ntype, self.n_etype, node_type.size(1), True,
-                          allow_general_fallback=True)
+                self.check_batch(A, node_type)
             side = torch.cuda.Stream(device=H.device)
             side.wait_stream(torch.cuda.current_stream(H.device))
             with torch.cuda.stream(side):
@@ -569,10 +594,10 @@ class LM_QAGNN(nn.Module):
         flat = [x.reshape(x.size(0) * x.size(1), *x.size()[2:]) for x in inputs[:-2]]
         *lm_inputs, concept_ids, node_type_ids, node_scores, adj_lengths = flat
         if isinstance(edge_index_orig, PackedAdj):  # pre-packed batch (qagnn_b200.data.pack_adj); edge_type slot unused
-            edge_index, edge_type = edge_index_orig.edge_index, edge_index_orig.edge_type
+            adj = edge_index_orig.to(node_type_ids.device)  # keeps graph_ptr: graph prep is then one launch per batch
         else:
             edge_index, edge_type = self.batch_graph(sum(edge_index_orig, []), sum(edge_type_orig, []), concept_ids.size(1))
-        adj = (edge_index.to(node_type_ids.device), edge_type.to(node_type_ids.device))
+            adj = (edge_index.to(node_type_ids.device), edge_type.to(node_type_ids.device))
         sent_vecs, all_hidden_states = self.encoder(*lm_inputs, layer_id=layer_id)
         logits, attn = self.decoder(sent_vecs.to(node_type_ids.device), concept_ids, node_type_ids, node_scores,
                                     adj_lengths, adj, emb_data=None, cache_output=cache_output)

@@ -26,10 +26,19 @@ class DecoderStep:
     `logits` [world*B, 1] (every rank holds all of them), `pool_attn` [n_head*B, n], `gnn_out` [B,n,D]."""
 
     FIELDS = ("H", "edge_index", "edge_type", "node_type", "node_score", "sent_vecs", "adj_lengths")
+    PACKED_FIELDS = FIELDS + ("graph_ptr",)  # + first edge of every sub-graph, int64 [B + 1] (packed batches)
 
-    def __init__(self, gnn, pooler, fc, inputs, world_size=1, group=None, use_cuda_graph=True):
+    def __init__(self, gnn, pooler, fc, inputs, world_size=1, group=None, use_cuda_graph=True, max_edges=-1):
+        """`inputs` may carry "graph_ptr" (device int64 [B + 1]) with `max_edges` = an upper bound of the edges of one sub-graph
+        for every batch that will be written into these buffers: graph prep is then ONE launch (qagnn_graph_prep_packed)."""
         self.gnn, self.pooler, self.fc = gnn, pooler, fc
         self.inp = {k: inputs[k] for k in self.FIELDS}
+        self.adj = (self.inp["edge_index"], self.inp["edge_type"])
+        if "graph_ptr" in inputs and max_edges >= 0:
+            from .data import PackedAdj
+            self.inp["graph_ptr"] = inputs["graph_ptr"]
+            self.adj = PackedAdj(self.inp["edge_index"], self.inp["edge_type"], None, self.inp["H"].size(1), None,
+                                 self.inp["graph_ptr"], int(max_edges))
         self.world, self.group = world_size, group
         dev = self.inp["H"].device
         B, n, D = self.inp["H"].shape
@@ -44,7 +53,7 @@ class DecoderStep:
     @torch.no_grad()
     def _eager(self):
         d = self.inp
-        out = self.gnn(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+        out = self.gnn(d["H"], self.adj, d["node_type"], d["node_score"])
         fused = self.pooler.pool_concat(d["sent_vecs"], out, d["node_type"], d["adj_lengths"])  # :172-187 in one kernel
         if fused is not None:
             concat, pool_attn = fused
@@ -66,7 +75,7 @@ class DecoderStep:
         try:
             if check:  # validate once, eagerly (a synchronising call), before trusting the capture
                 self.gnn.check_indices = True
-                self.gnn.prepare_graph(self.inp["edge_index"], self.inp["edge_type"], self.inp["node_type"])
+                self.gnn.check_batch(self.adj, self.inp["node_type"])
                 self.gnn.check_indices = False
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))

@@ -24,12 +24,26 @@ def _dev(inp):
     return {k: v.to(DEV) for k, v in inp.items()}
 
 
+def _graph_ptr(edge_index, n, B):
+    """first edge of every sub-graph of a batch whose edges are laid out graph by graph"""
+    cnt = torch.bincount(edge_index[0] // n, minlength=B)
+    gp = torch.zeros(B + 1, dtype=torch.long)
+    gp[1:] = torch.cumsum(cnt, 0)
+    return gp
+
+
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("name", Hh.golden_names("mp"))
-def test_graph_prep_bit_exact(name):
+def test_graph_prep_bit_exact(name, packed):
+    """packed=True: the one-launch per-sub-graph kernel (qagnn_graph_prep_packed) must give the same arrays, bit for bit."""
     fx = Hh.load_golden(name)
     inp, _ = Hh.regen_mp_inputs(fx)
     d = _dev(inp)
-    prep = GraphPrep(d["edge_index"], d["edge_type"], d["node_type"], fx["n_ntype"], fx["n_etype"], fx["case"]["n"])
+    kw = {}
+    if packed:
+        gp = _graph_ptr(inp["edge_index"], fx["case"]["n"], fx["case"]["B"])
+        kw = dict(graph_ptr=gp.to(DEV), max_edges=int((gp[1:] - gp[:-1]).max()) if gp.numel() > 1 else 0)
+    prep = GraphPrep(d["edge_index"], d["edge_type"], d["node_type"], fx["n_ntype"], fx["n_etype"], fx["case"]["n"], **kw)
     ref = O.graph_prep_oracle(inp["edge_index"], inp["edge_type"], inp["node_type"], fx["n_ntype"], fx["n_etype"])
     got = {k: prep.array(k).cpu().numpy().astype(np.int64) for k in
            ("src", "tgt", "combo", "rowptr_src", "rowptr_tgt", "perm_src", "perm_tgt", "csr_src_tgt", "csr_src_combo",
@@ -223,6 +237,35 @@ def test_cross_graph_edge_is_rejected_when_n_per_graph_is_given():
     GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=0)  # legal for a general graph
     with pytest.raises(IndexError):
         GraphPrep(bad, d["edge_type"], d["node_type"], 4, 38, n_per_graph=10)
+
+
+def test_packed_batch_through_the_module_matches_the_unpacked_call_and_rejects_bad_graph_ptr():
+    """A qagnn_b200.data.PackedAdj (graph_ptr + max_edges) in place of the (edge_index, edge_type) pair: same output bits; a
+    graph_ptr that disagrees with the edges is an IndexError, a cross-graph edge falls back to the general prep."""
+    from qagnn_b200.data import PackedAdj
+    B, n, D, k = 5, 30, 64, 2
+    inp = O.synth_graph_batch(B, n, 70, D, 38, 4, realistic=True)
+    sd = O.random_state_dict(k, D, 4, 38, "peaky", 4)
+    mod = qagnn_b200.QAGNN_Message_Passing(None, k, 4, 38, D, D, D).eval()
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    d = _dev(inp)
+    gp = _graph_ptr(inp["edge_index"], n, B)
+    plain = mod(d["H"], (d["edge_index"], d["edge_type"]), d["node_type"], d["node_score"])
+    pk = PackedAdj(d["edge_index"], d["edge_type"], gp, n, None, gp.to(DEV), int((gp[1:] - gp[:-1]).max()))
+    packed = mod(d["H"], pk, d["node_type"], d["node_score"])
+    assert torch.equal(plain, packed)
+    assert mod._last_prep.n_per_graph == n
+    mod.use_cuda_graph = True  # and through the module's own CUDA-graph cache
+    assert torch.equal(mod(d["H"], pk, d["node_type"], d["node_score"]), plain)
+    mod.use_cuda_graph = False
+    bad_gp = gp.clone(); bad_gp[2] += 3  # sub-graph 1 claims 3 edges of sub-graph 2
+    with pytest.raises(IndexError):
+        GraphPrep(d["edge_index"], d["edge_type"], d["node_type"].view(-1), 4, 38, n, graph_ptr=bad_gp.to(DEV),
+                  max_edges=int((bad_gp[1:] - bad_gp[:-1]).max()))
+    short = PackedAdj(d["edge_index"], d["edge_type"], gp, n, None, gp.to(DEV), 3)  # max_edges too small: refused, not overrun
+    with pytest.raises(IndexError):
+        mod(d["H"], short, d["node_type"], d["node_score"])
 
 
 def test_cross_graph_edges_fall_back_to_the_general_kernels_in_the_module_api():
