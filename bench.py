@@ -301,7 +301,8 @@ def run_b200_arm(args):
             for r in range(world):
                 ri = synth_step_inputs(r)
                 rd = {k_: ri[k_].to(dev) for k_ in DecoderStep.PACKED_FIELDS}
-                refs.append(DecoderStep(mod, pooler, fc, rd, 1, None, use_cuda_graph=False, max_edges=max_edges).run()[0])
+                refs.append(DecoderStep(mod, pooler, fc, rd, 1, None, use_cuda_graph=False,
+                                        max_edges=int((ri["graph_ptr"][1:] - ri["graph_ptr"][:-1]).max())).run()[0])
             ref = torch.cat(refs)
             logits_err = (got - ref).abs().max().item()
             if logits_err > 1e-5 + 1e-5 * ref.abs().max().item():
