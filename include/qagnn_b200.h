@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define QAGNN_ABI_VERSION 2
+#define QAGNN_ABI_VERSION 3 /* 3: + training core, packed graph prep, decoder head / tail (round 2) */
 
 enum {
   QAGNN_OK = 0,

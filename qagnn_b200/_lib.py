@@ -105,7 +105,7 @@ def load():
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.qagnn_abi_version() != 2:
+    if lib.qagnn_abi_version() != 3:
         raise RuntimeError("libqagnn_b200.so ABI version mismatch")
     _lib = lib
     return lib

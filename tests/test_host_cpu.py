@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/qagnn_b200.h but not exported"
     assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
-    assert lib.qagnn_abi_version() == 2
+    assert lib.qagnn_abi_version() == 3
     assert lib.qagnn_status_string(-3).decode().startswith("index out of range")
 
 
@@ -83,3 +83,17 @@ def test_pack_adj_equals_batch_graph():
     assert packed.graph_ptr[-1] == ref_ei.size(1)
     lm = qagnn_b200.LM_QAGNN.batch_graph(None, sum(ei, []), sum(et, []), n)
     assert torch.equal(lm[0], ref_ei) and torch.equal(lm[1], ref_et)
+
+
+def test_packed_adj_behaves_as_an_edge_pair_and_keeps_graph_ptr():
+    """PackedAdj stands in for the (edge_index, edge_type) pair everywhere (unpacking, indexing) and carries what the
+    one-launch graph prep needs (graph_ptr on the device of the edges, the largest sub-graph's edge count)."""
+    ei = [[torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 0, dtype=torch.long)], [torch.tensor([[3], [0]]), torch.tensor([[1, 1, 2], [0, 2, 2]])]]
+    et = [[torch.tensor([5, 6]), torch.zeros(0, dtype=torch.long)], [torch.tensor([7]), torch.tensor([1, 2, 3])]]
+    p = pack_adj(ei, et, 4, pin=False)
+    a, b = p
+    assert a is p.edge_index and b is p.edge_type and p[0] is a and p[1] is b and len(p) == 2
+    assert p.graph_ptr.tolist() == [0, 2, 2, 3, 6]
+    assert p.edge_index.tolist() == [[0, 1, 11, 13, 13, 14], [1, 2, 8, 12, 14, 14]]
+    q = p.to("cpu")
+    assert q.max_edges == 3 and torch.equal(q.graph_ptr_dev, p.graph_ptr) and torch.equal(q.edge_index, p.edge_index)
