@@ -83,9 +83,13 @@ def cfg3():
         adj = (packed.edge_index, packed.edge_type)
         d2 = [x.view(bs * nc, *x.shape[2:]) for x in dec]
         dec_ms = gpu_time(lambda: model.decoder(sent, *d2, adj), 10, warm=3)
+        dec_packed_ms = gpu_time(lambda: model.decoder(sent, *d2, packed), 10, warm=3)  # graph_ptr known: one-launch prep
+        Hin = torch.randn(bs * nc, n, D, device=dev) * 0.5
+        mp_ms = gpu_time(lambda: model.decoder.gnn(Hin, packed, d2[1], d2[2]), 10, warm=3)
     E = packed.edge_index.size(1)
     return {"config": "cfg3: LM_QAGNN forward, RoBERTa-large random init fp32 (24L/1024h), 64x5 x 100 tokens, loader-shaped "
                       "synthetic adj.pk, k=5, D=200", "full_forward_ms": full_ms, "encoder_ms": enc_ms, "decoder_ms": dec_ms,
+            "decoder_ms_packed_batch": dec_packed_ms, "message_passing_only_ms": mp_ms, "decoder_over_message_passing": dec_packed_ms / mp_ms,
             "qa_pairs_per_s_full": bs * nc / (full_ms * 1e-3), "qa_pairs_per_s_decoder_only": bs * nc / (dec_ms * 1e-3),
             "gnn_share_of_forward": dec_ms / full_ms, "edges_in_batch": E, "loader_s_for_320_records": load_s}
 
