@@ -76,3 +76,12 @@ def test_shard_bounds_cover_the_batch():
             spans = [D.shard_bounds(B, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    """bind_to_gpu_numa_node is an optimisation: on a host without CUDA devices (or without NUMA information) it must return
+    None and leave the process affinity alone."""
+    before = os.sched_getaffinity(0)
+    assert D.bind_to_gpu_numa_node(0) is None or isinstance(D.bind_to_gpu_numa_node(0), int)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before

@@ -33,8 +33,5 @@ for (M, K1, K2, N, act) in [(64000, 200, 200, 600, "none"), (64000, 200, 0, 200,
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    if os.environ.get("QAGNN_TC_DEBUG"):
-        print(f"debug={os.environ['QAGNN_TC_DEBUG']} M={M} K={K1}+{K2} N={N}: {ms*1e3:.1f} us")
-        continue
     print(f"M={M} K={K1}+{K2} N={N} act={act}: max|err| {err:.2e} (torch fp32 matmul: {err32:.2e}); {ms*1e3:.1f} us incl. operand split "
           f"({2*M*(K1+K2)*N/ms/1e9:.1f} TFLOP/s effective)")
