@@ -4,6 +4,8 @@ import os
 import subprocess
 import sys
 
+import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -26,3 +28,31 @@ def test_reference_arm_is_silent_on_other_ranks():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                          text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_traffic_artefact_belongs_to_the_current_kernel_source():
+    """bench.py reports roofline.traffic only from profiles/mp_traffic.json and only while its sha matches mp_headtile.cu:
+    the committed artefact must be the capture of the committed kernel (else the field silently becomes null)."""
+    import bench
+    sha = bench.mp_kernel_sha()
+    traffic = bench.mp_traffic_from_profile(sha)
+    assert traffic is not None and 150e6 < traffic < 260e6, "re-capture profiles/mp_traffic.json after changing mp_headtile.cu"
+    assert bench.mp_traffic_from_profile("0" * 16) is None
+
+
+def test_oracle_slice_equals_the_full_batch_rows():
+    """The parity gate of bench.py evaluates the oracle on a slice of the batch; sub-graphs are independent, so the slice must
+    reproduce the corresponding rows of a full-batch oracle run (small shape)."""
+    import bench
+    from oracle import qagnn_oracle as O
+    saved = dict(bench.CFG)
+    try:
+        bench.CFG.update(graphs=6, n=20, e=40, D=16, k=2, H=4)
+        inp = O.synth_graph_batch(6, 20, 40, 16, bench.CFG["R"], seed=1)
+        sd = O.random_state_dict(2, 16, bench.CFG["T"], bench.CFG["R"], "peaky", seed=1)
+        full = O.message_passing_forward(sd, inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"], inp["node_score"], 2,
+                                         bench.CFG["T"], bench.CFG["R"], 4)
+        part = bench.oracle_slice(inp, sd, 2, 3)
+        assert torch.allclose(part, full[2:5], atol=1e-6, rtol=1e-6)
+    finally:
+        bench.CFG.clear(); bench.CFG.update(saved)
