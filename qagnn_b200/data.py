@@ -223,6 +223,26 @@ class FlatAdjCache:
     def n_graphs(self):
         return len(self.graph_ptr) - 1
 
+    def n_questions(self):
+        return self.n_graphs() // self.num_choice
+
+    def __getitem__(self, i):
+        """What LM_QAGNN_DataLoader does with `adj_data` besides handing it to the batch generator
+        (modeling_qagnn.py:281-287,307-308): `len(adj_data[0])` must be the number of questions, and `adj_data[:n]` is taken
+        when a split is subsampled.  An int gives a sized stand-in for the nested list, a slice the cache of those questions."""
+        if isinstance(i, slice):
+            a, b, step = i.indices(self.n_questions())
+            if step != 1:
+                raise IndexError("FlatAdjCache supports contiguous question ranges only")
+            b = max(a, b)
+            g0, g1 = a * self.num_choice, b * self.num_choice
+            e0, e1 = int(self.graph_ptr[g0]), int(self.graph_ptr[g1])
+            return FlatAdjCache(self.src[e0:e1], self.tgt[e0:e1], self.etype[e0:e1],
+                                np.asarray(self.graph_ptr[g0:g1 + 1]) - e0, self.num_choice, self.n_nodes)
+        if i in (0, 1, -1, -2):
+            return range(self.n_questions())
+        raise IndexError("FlatAdjCache stands in for the (edge_index, edge_type) pair: index 0 or 1")
+
     def pack(self, question_indexes, pin=True):
         """PackedAdj of the questions `question_indexes` (all their choices, in order) — equal to
         LM_QAGNN.batch_graph applied to the corresponding nested-list slice (modeling_qagnn.py:244-251)."""

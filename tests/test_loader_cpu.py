@@ -83,6 +83,28 @@ def test_flat_cache_pack_equals_batch_graph_of_the_nested_lists(tmp_path):
     assert torch.equal(out[4].pack([1]).edge_index, Dt.pack_adj([ei[1]], [et[1]], n, pin=False).edge_index)
 
 
+def test_flat_cache_answers_what_the_reference_dataloader_asks_of_adj_data(tmp_path):
+    """LM_QAGNN_DataLoader (modeling_qagnn.py:281-287,307-308) takes len(adj_data[0]) and adj_data[:n_train]."""
+    n, nc = 40, 5
+    path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 30, n, nc)
+    flat = Dt.FlatAdjCache.from_nested(ei, et, n)
+    assert len(flat[0]) == len(ei) == cids.size(0) and len(flat[1]) == len(et)
+    head = flat[:4]
+    assert head.n_questions() == 4 and len(head[0]) == 4
+    for idx in ([0, 3], [2]):
+        want = Dt.pack_adj([ei[i] for i in idx], [et[i] for i in idx], n, pin=False)
+        got = head.pack(idx, pin=False)
+        assert torch.equal(got.edge_index, want.edge_index) and torch.equal(got.edge_type, want.edge_type)
+    mid = flat[2:5]
+    want = Dt.pack_adj([ei[3]], [et[3]], n, pin=False)
+    assert torch.equal(mid.pack([1], pin=False).edge_index, want.edge_index)
+    assert flat[6:6].n_questions() == 0
+    with pytest.raises(IndexError):
+        flat[2]
+    with pytest.raises(IndexError):
+        flat[::2]
+
+
 def test_packed_batch_generator_matches_reference_generator(tmp_path):
     n, nc, bs = 40, 5, 4
     path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 50, n, nc)  # 10 questions
