@@ -287,26 +287,68 @@ class PackedAdjBatchGenerator:
     well, so every copy of a batch is asynchronous.  With nested-list `adj_data` it behaves exactly like the reference."""
 
     def __init__(self, args, mode, device0, device1, batch_size, indexes, qids, labels, tensors0=[], lists0=[], tensors1=[],
-                 lists1=[], adj_data=None):
+                 lists1=[], adj_data=None, prefetch=0):
+        """`prefetch` > 0 (not in the reference): a worker thread slices / packs / pins up to that many batches ahead on the
+        host while the consumer trains on the current one; the device copies are still issued by the consuming thread (on
+        ITS current stream), in order, so the batches and their order are exactly those of prefetch=0."""
         self.args, self.mode = args, mode
         self.device0, self.device1 = device0, device1
         self.batch_size, self.indexes, self.qids, self.labels = batch_size, indexes, qids, labels
         self.tensors0, self.lists0, self.tensors1, self.lists1 = tensors0, lists0, tensors1, lists1
         self.adj_data = adj_data
+        self.prefetch = int(prefetch)
 
     def __len__(self):
         return (self.indexes.size(0) - 1) // self.batch_size + 1
+
+    @staticmethod
+    def _pin(obj, device):
+        """Host side of a copy: page-locks a tensor bound for a CUDA device (nested lists element-wise)."""
+        if isinstance(obj, (tuple, list)):
+            return [PackedAdjBatchGenerator._pin(item, device) for item in obj]
+        if isinstance(obj, PackedAdj):
+            return obj  # FlatAdjCache.pack already wrote it into pinned memory
+        if torch.cuda.is_available() and torch.device(device).type == "cuda" and not obj.is_pinned():
+            return obj.pin_memory()
+        return obj
 
     def _to_device(self, obj, device):
         if isinstance(obj, (tuple, list)):
             return [self._to_device(item, device) for item in obj]
         if isinstance(obj, PackedAdj):
             return obj.to(device, non_blocking=True)
-        if torch.cuda.is_available() and torch.device(device).type == "cuda" and not obj.is_pinned():
-            obj = obj.pin_memory()
-        return obj.to(device, non_blocking=True)
+        return self._pin(obj, device).to(device, non_blocking=True)
 
-    def __iter__(self):
+    def _host_batch(self, batch_indexes):
+        """Everything of one batch that needs no device: slicing, adjacency packing, pinning."""
+        d0, d1 = self.device0, self.device1
+        qids = [self.qids[idx] for idx in batch_indexes]
+        labels = self._pin(self.labels[batch_indexes], d1)
+        tensors0 = [self._pin(x[batch_indexes], d0) for x in self.tensors0]
+        tensors1 = [self._pin(x[batch_indexes], d1) for x in self.tensors1]
+        lists0 = [self._pin([x[i] for i in batch_indexes], d0) for x in self.lists0]
+        lists1 = [self._pin([x[i] for i in batch_indexes], d1) for x in self.lists1]
+        if isinstance(self.adj_data, FlatAdjCache):
+            adj = self.adj_data.pack(batch_indexes.numpy())
+        else:
+            edge_index_all, edge_type_all = self.adj_data
+            adj = (self._pin([edge_index_all[i] for i in batch_indexes], d1),
+                   self._pin([edge_type_all[i] for i in batch_indexes], d1))
+        return qids, labels, tensors0, lists0, tensors1, lists1, adj
+
+    def _ship(self, host):
+        qids, labels, tensors0, lists0, tensors1, lists1, adj = host
+        d0, d1 = self.device0, self.device1
+        if isinstance(adj, PackedAdj):
+            packed = self._to_device(adj, d1)
+            edge_index, edge_type = packed, packed.edge_type
+        else:
+            edge_index, edge_type = self._to_device(adj[0], d1), self._to_device(adj[1], d1)
+        return tuple([qids, self._to_device(labels, d1), *[self._to_device(x, d0) for x in tensors0],
+                      *[self._to_device(x, d0) for x in lists0], *[self._to_device(x, d1) for x in tensors1],
+                      *[self._to_device(x, d1) for x in lists1], edge_index, edge_type])
+
+    def _batch_ranges(self):
         bs = self.batch_size
         n = self.indexes.size(0)
         if self.mode == "train" and getattr(self.args, "drop_partial_batch", False):
@@ -317,21 +359,47 @@ class PackedAdjBatchGenerator:
                 extra = np.random.choice(self.indexes[:-remain], size=(bs - remain), replace=False)
                 self.indexes = torch.cat([self.indexes, torch.tensor(extra)])
                 n = self.indexes.size(0)
-        for a in range(0, n, bs):
-            b = min(n, a + bs)
-            batch_indexes = self.indexes[a:b]
-            batch_qids = [self.qids[idx] for idx in batch_indexes]
-            batch_labels = self._to_device(self.labels[batch_indexes], self.device1)
-            batch_tensors0 = [self._to_device(x[batch_indexes], self.device0) for x in self.tensors0]
-            batch_tensors1 = [self._to_device(x[batch_indexes], self.device1) for x in self.tensors1]
-            batch_lists0 = [self._to_device([x[i] for i in batch_indexes], self.device0) for x in self.lists0]
-            batch_lists1 = [self._to_device([x[i] for i in batch_indexes], self.device1) for x in self.lists1]
-            if isinstance(self.adj_data, FlatAdjCache):
-                packed = self._to_device(self.adj_data.pack(batch_indexes.numpy()), self.device1)
-                edge_index, edge_type = packed, packed.edge_type
-            else:
-                edge_index_all, edge_type_all = self.adj_data
-                edge_index = self._to_device([edge_index_all[i] for i in batch_indexes], self.device1)
-                edge_type = self._to_device([edge_type_all[i] for i in batch_indexes], self.device1)
-            yield tuple([batch_qids, batch_labels, *batch_tensors0, *batch_lists0, *batch_tensors1, *batch_lists1,
-                         edge_index, edge_type])
+        return [self.indexes[a:min(n, a + bs)] for a in range(0, n, bs)]
+
+    def __iter__(self):
+        batches = self._batch_ranges()
+        if self.prefetch <= 0:
+            for batch_indexes in batches:
+                yield self._ship(self._host_batch(batch_indexes))
+            return
+        import queue
+        import threading
+        q = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+
+        def put(item):  # a consumer that stops iterating early must not leave the worker blocked on a full queue
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    pass
+            return False
+
+        def work():
+            try:
+                for batch_indexes in batches:
+                    if not put(("batch", self._host_batch(batch_indexes))):
+                        return
+                put(("end", None))
+            except BaseException as e:  # surfaces in the consuming thread
+                put(("error", e))
+
+        t = threading.Thread(target=work, name="qagnn-batch-prefetch", daemon=True)
+        t.start()
+        try:
+            while True:
+                kind, item = q.get()
+                if kind == "end":
+                    break
+                if kind == "error":
+                    raise item
+                yield self._ship(item)
+        finally:
+            stop.set()
+            t.join()

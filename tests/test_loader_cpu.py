@@ -141,3 +141,64 @@ def test_packed_batch_generator_matches_reference_generator(tmp_path):
         want = Dt.pack_adj(br[-2], br[-1], n, pin=False)  # == LM_QAGNN.batch_graph of the reference's nested batch
         assert isinstance(bo[-2], Dt.PackedAdj)
         assert torch.equal(bo[-2].edge_index, want.edge_index) and torch.equal(bo[-1], want.edge_type)
+
+
+def _batches_equal(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x[0] == y[0]
+        for u, v in zip(x[1:-2], y[1:-2]):
+            assert torch.equal(u, v)
+        if isinstance(x[-2], Dt.PackedAdj):
+            assert torch.equal(x[-2].edge_index, y[-2].edge_index) and torch.equal(x[-2].graph_ptr, y[-2].graph_ptr)
+            assert torch.equal(x[-1], y[-1])
+        else:
+            assert _equal_nested(x[-2], y[-2]) and _equal_nested(x[-1], y[-1])
+
+
+@pytest.mark.parametrize("mode,drop,fill", [("eval", False, False), ("train", True, False), ("train", False, True)])
+def test_prefetching_generator_yields_the_same_batches_in_the_same_order(tmp_path, mode, drop, fill):
+    import numpy as np
+    import threading
+    n, nc, bs = 40, 5, 4
+    path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 55, n, nc)  # 11 questions: a partial last batch
+    Q = cids.size(0)
+    qids = [f"q{i}" for i in range(Q)]
+    labels = torch.arange(Q) % nc
+    indexes = torch.randperm(Q, generator=torch.Generator().manual_seed(1))
+
+    class Args:
+        drop_partial_batch = drop
+        fill_partial_batch = fill
+    kw = dict(tensors0=[torch.arange(Q * nc).view(Q, nc)], tensors1=[cids, ntypes, scores, lens])
+    flat = Dt.FlatAdjCache.from_nested(ei, et, n)
+    for adj in (flat, (ei, et)):
+        np.random.seed(5)
+        plain = list(Dt.PackedAdjBatchGenerator(Args(), mode, "cpu", "cpu", bs, indexes, qids, labels, adj_data=adj, **kw))
+        np.random.seed(5)
+        ahead = list(Dt.PackedAdjBatchGenerator(Args(), mode, "cpu", "cpu", bs, indexes, qids, labels, adj_data=adj,
+                                                prefetch=2, **kw))
+        _batches_equal(plain, ahead)
+        assert len(plain) == (Q // bs if drop else (Q + bs - 1) // bs)
+    # a consumer that stops early does not leave the worker thread behind
+    before = threading.active_count()
+    it = iter(Dt.PackedAdjBatchGenerator(Args(), "eval", "cpu", "cpu", 2, indexes, qids, labels, adj_data=flat, prefetch=1, **kw))
+    next(it)
+    it.close()
+    assert threading.active_count() == before
+
+
+def test_prefetching_generator_reraises_worker_errors(tmp_path):
+    n, nc = 40, 5
+    path, (cids, ntypes, scores, lens, (ei, et)) = _make_split(tmp_path, 20, n, nc)
+    Q = cids.size(0)
+    bad = torch.tensor([0, 1, Q + 3])  # question Q+3 does not exist
+
+    class Args:
+        pass
+    gen = Dt.PackedAdjBatchGenerator(Args(), "eval", "cpu", "cpu", 2, bad, [f"q{i}" for i in range(Q + 4)], torch.zeros(Q + 4),
+                                     tensors1=[], adj_data=Dt.FlatAdjCache.from_nested(ei, et, n), prefetch=2)
+    it = iter(gen)
+    next(it)
+    with pytest.raises(IndexError):
+        next(it)
