@@ -156,3 +156,44 @@ def test_oracle_attention_sums_to_one_per_source_and_rescale_is_the_out_degree()
     assert torch.allclose(l2[0]["alpha"][0], l2[0]["alpha"][ei.size(1)], atol=0)
     assert np.array_equal(O.graph_prep_oracle(dup["edge_index"], dup["edge_type"], b["node_type"].reshape(-1), 4, R)["outdeg"],
                           prep["outdeg"] + np.bincount([int(ei[0, 0])], minlength=B * n))
+
+
+def _core_forward(Q, Kx, Mx, Ke, Me, src, tgt, combo, outdeg, N):
+    """The graph part of a layer on node-level projections (what qagnn_mp_core_forward evaluates), in autograd-able torch ops."""
+    s = (Q[src] * (Kx[tgt] + Ke[combo])).sum(-1)
+    a = O.segment_softmax(s, src)
+    a_scaled = a * outdeg[src][:, None]
+    aggr = torch.zeros(N, *Q.shape[1:], dtype=F64).index_add_(0, tgt, a_scaled[:, :, None] * (Mx[src] + Me[combo]))
+    return aggr, a, a_scaled
+
+
+@pytest.mark.parametrize("seed,B,n,e", [(0, 3, 9, 30), (1, 2, 6, 0), (2, 1, 1, 4)])
+def test_backward_formulas_of_the_graph_part_equal_autograd(seed, B, n, e):
+    """da' = G[tgt]·(Mx[src]+Me[c]); ds = a(da − Σ_src a·da) with da = outdeg·da'; dQ / dKx / dKe from ds,
+    dMx / dMe from a'·G — the closed forms mp_bwd_source / _target / _table_kernel implement, against autograd."""
+    T, R, H, d = 4, 7, 2, 5
+    b = O.synth_graph_batch(B, n, e, H * d, n_etype=R, seed=seed)
+    N = B * n
+    prep = O.graph_prep_oracle(b["edge_index"], b["edge_type"], b["node_type"].reshape(-1), T, R)
+    src, tgt, combo = (torch.from_numpy(prep[k]) for k in ("src", "tgt", "combo"))
+    outdeg = torch.from_numpy(prep["outdeg"]).to(F64)
+    g = torch.Generator().manual_seed(seed)
+    C = R * T * T + T
+    Q, Kx, Mx = (torch.randn(N, H, d, dtype=F64, generator=g, requires_grad=True) for _ in range(3))
+    Ke, Me = (torch.randn(C, H, d, dtype=F64, generator=g, requires_grad=True) for _ in range(2))
+    G = torch.randn(N, H, d, dtype=F64, generator=g)
+    aggr, a, a_scaled = _core_forward(Q, Kx, Mx, Ke, Me, src, tgt, combo, outdeg, N)
+    want = torch.autograd.grad(aggr, (Q, Kx, Mx, Ke, Me), G)
+    with torch.no_grad():
+        da_scaled = (G[tgt] * (Mx[src] + Me[combo])).sum(-1)                     # [E', H]
+        da = da_scaled * outdeg[src][:, None]
+        dot = torch.zeros(N, H, dtype=F64).index_add_(0, src, a * da)            # Σ over the edges of one source
+        ds = a * (da - dot[src])
+        zeros = lambda rows: torch.zeros(rows, H, d, dtype=F64)                  # noqa: E731
+        dQ = zeros(N).index_add_(0, src, ds[:, :, None] * (Kx[tgt] + Ke[combo]))
+        dKx = zeros(N).index_add_(0, tgt, ds[:, :, None] * Q[src])
+        dKe = zeros(C).index_add_(0, combo, ds[:, :, None] * Q[src])
+        dMx = zeros(N).index_add_(0, src, a_scaled[:, :, None] * G[tgt])
+        dMe = zeros(C).index_add_(0, combo, a_scaled[:, :, None] * G[tgt])
+    for name, got, w in zip(("dQ", "dKx", "dMx", "dKe", "dMe"), (dQ, dKx, dMx, dKe, dMe), want):
+        assert torch.allclose(got, w, rtol=1e-9, atol=1e-9), name
