@@ -4,6 +4,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,3 +57,41 @@ def test_oracle_slice_equals_the_full_batch_rows():
         assert torch.allclose(part, full[2:5], atol=1e-6, rtol=1e-6)
     finally:
         bench.CFG.clear(); bench.CFG.update(saved)
+
+
+def _bench_lines(path):
+    import json
+    return [json.loads(l) for l in open(path) if l.strip().startswith("{")]
+
+
+@pytest.mark.parametrize("name", ["r2_final_bench.json", "r2_bench_n2.json", "r2_bench_n4.json", "r2_bench_n8.json"])
+def test_committed_bench_lines_are_self_consistent(name):
+    """The arithmetic a reader redoes on a bench line: throughput from ms_per_step, roofline from B_alg."""
+    path = os.path.join(ROOT, "profiles", name)
+    lines = _bench_lines(path)
+    assert lines, path
+    d = lines[-1]
+    k, D = 5, 200
+    N, E, G = d["config"]["N"], d["config"]["E"], d["n_gpus"]
+    assert d["metric"] == "GNN edges/sec" and d["scaling"] == "weak" and d["dtype"] == "f32" and d["vs_baseline"] is None
+    assert d["value"] == pytest.approx(G * k * E / (d["ms_per_step"] * 1e-3), rel=1e-6)
+    assert d["e2e"]["value"] == pytest.approx(G * k * E / (d["e2e"]["ms_per_step"] * 1e-3), rel=1e-6)
+    assert d["e2e"]["value"] < d["value"] and d["e2e"]["h2d_bytes_per_step"] > 8 * 2 * E and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["algorithmic_bytes_per_launch"] == 16 * N * D + 24 * E + 8 * N == 212992000     # SURVEY.md §8d
+    assert r["achieved"] == pytest.approx(r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9, rel=1e-6)
+    assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and r["bound"] == "hbm"
+    assert r["traffic"] is None or 0.5 * r["algorithmic_bytes_per_launch"] < r["traffic"] < 1.5 * r["algorithmic_bytes_per_launch"]
+    assert k * r["avg_launch_ms"] < d["ms_per_step"]                                        # the kernel fits k times in the step
+    st = d["stages"]
+    assert st["message_passing"]["ms_per_step"] == pytest.approx(k * r["avg_launch_ms"], rel=1e-3)
+    assert sum(s["ms_per_step"] for s in st.values()) < d["ms_per_step_per_kernel_launches"]
+    gm = d["roofline_gemm"]
+    assert gm["frac"] == pytest.approx(gm["achieved"] / gm["peak"], rel=1e-9)
+    if "flops_per_launch" in gm:  # the 8-GPU line predates this key
+        assert gm["flops_per_launch"] == 3 * 2 * N * (D + D // 2) * 624                      # three bf16 passes, padded 3*H*DP columns
+        assert gm["achieved"] == pytest.approx(gm["flops_per_launch"] / (gm["avg_launch_ms"] * 1e-3) / 1e12, rel=1e-6)
+    assert d["gpu_launches"] > 0 and d["parity_gate"]["max_abs_err"] < 1e-4
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if G > 1:
+        assert d["parity_gate"]["multi_rank_logits_vs_single_gpu_max_abs_err"] < 1e-5
