@@ -12,7 +12,7 @@ import torch.nn as nn
 class TextEncoder(nn.Module):
     def __init__(self, model_name, output_token_states=False, from_checkpoint=None, config=None, **kwargs):
         super().__init__()
-        from transformers import AutoConfig, AutoModel
+        from transformers import AutoModel
         self.output_token_states = output_token_states
         if config is not None:
             config.output_hidden_states = True
