@@ -34,6 +34,42 @@ def test_header_symbols_are_exported(lib):
     assert lib.qagnn_status_string(-3).decode().startswith("index out of range")
 
 
+def _c_kind(decl):
+    """Coarse ctypes class of one C parameter / return type as written in the header."""
+    decl = re.sub(r"/\*.*?\*/", "", decl).strip()
+    if "*" in decl:
+        return "char*" if re.match(r"(const\s+)?char\s*\*", decl) else "ptr"
+    for t in ("int64_t", "int32_t", "size_t", "double", "float"):
+        if re.search(rf"\b{t}\b", decl):
+            return t
+    raise AssertionError(f"unparsed C type: {decl!r}")
+
+
+def _ctypes_kind(t):
+    if t is C.c_char_p:
+        return "char*"
+    if t is C.c_void_p or (isinstance(t, type) and issubclass(t, C._Pointer)):
+        return "ptr"
+    return {C.c_int64: "int64_t", C.c_int32: "int32_t", C.c_size_t: "size_t", C.c_double: "double", C.c_float: "float"}[t]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/qagnn_b200.h against the ctypes binding: return type, parameter count, and per parameter
+    pointer vs integer width (a drifted binding corrupts the call frame silently)."""
+    header = open(os.path.join(ROOT, "include", "qagnn_b200.h")).read()
+    header = re.sub(r"//[^\n]*", "", header)
+    protos = re.findall(r"^((?:const\s+)?[a-z_0-9]+\s*\*?)\s*(qagnn_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.M | re.S)
+    assert len(protos) == len(_lib.EXPORTS), (len(protos), len(_lib.EXPORTS))
+    for ret, name, params in protos:
+        res, args = _lib.EXPORTS[name]
+        assert _c_kind(ret + " ") == _ctypes_kind(res), name
+        params = re.sub(r"/\*.*?\*/", "", params, flags=re.S).strip()
+        plist = [] if params in ("void", "") else [x.strip() for x in params.split(",")]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, binding {len(args)}"
+        for i, (pdecl, a) in enumerate(zip(plist, args)):
+            assert _c_kind(pdecl) == _ctypes_kind(a), f"{name}: parameter {i} ({pdecl})"
+
+
 def test_size_queries_and_argument_checks(lib):
     pl = _lib.PrepLayout()
     assert lib.qagnn_graph_prep_layout(64000, 320000, C.byref(pl)) == 0
