@@ -70,6 +70,29 @@ def test_ctypes_signatures_match_the_header_prototypes():
             assert _c_kind(pdecl) == _ctypes_kind(a), f"{name}: parameter {i} ({pdecl})"
 
 
+def test_ctypes_structs_match_the_header_structs():
+    """Field names, order and C type of every struct the ABI passes by pointer."""
+    header = open(os.path.join(ROOT, "include", "qagnn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    bind = {"qagnn_shape": _lib.Shape, "qagnn_edge_encoder_params": _lib.EdgeEncoderParams, "qagnn_layer_params": _lib.LayerParams,
+            "qagnn_mp_params": _lib.MPParams, "qagnn_prep_layout": _lib.PrepLayout}
+    structs = re.findall(r"typedef struct (qagnn_[a-z_]+) \{(.*?)\} \1;", header, flags=re.S)
+    assert {n for n, _ in structs} == set(bind)
+    for name, body in structs:
+        fields = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            ctype, names = re.match(r"((?:const\s+)?[a-z_0-9]+)\s+(.*)", stmt, flags=re.S).groups()
+            for nm in names.split(","):
+                nm = nm.strip()
+                fields.append((nm.lstrip("*").strip(), "ptr" if nm.startswith("*") else ctype))
+        got = [(n, _ctypes_kind(t)) for n, t in bind[name]._fields_]
+        assert got == fields, name
+    assert C.sizeof(_lib.Shape) == 40 and C.sizeof(_lib.PrepLayout) == 22 * C.sizeof(C.c_size_t)
+
+
 def test_size_queries_and_argument_checks(lib):
     pl = _lib.PrepLayout()
     assert lib.qagnn_graph_prep_layout(64000, 320000, C.byref(pl)) == 0
