@@ -156,3 +156,36 @@ def test_packed_adj_behaves_as_an_edge_pair_and_keeps_graph_ptr():
     assert p.edge_index.tolist() == [[0, 1, 11, 13, 13, 14], [1, 2, 8, 12, 14, 14]]
     q = p.to("cpu")
     assert q.max_edges == 3 and torch.equal(q.graph_ptr_dev, p.graph_ptr) and torch.equal(q.edge_index, p.edge_index)
+
+
+def test_header_is_plain_c99_and_the_library_links_from_a_c_program(lib, tmp_path):
+    """The drop-in boundary is a C ABI: a strict-C99 translation unit includes the header, links the in-tree library
+    (no torch, no CUDA runtime on the link line) and calls the entry points that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "qagnn_b200.h"
+int main(void) {
+  qagnn_shape s = {64000, 320000, 200, 4, 4, 38, 5, 200};
+  qagnn_prep_layout pl;
+  if (qagnn_graph_prep_layout(s.N, s.E, &pl) != QAGNN_OK) return 2;
+  printf("%d %lu %lu %lu\n", (int)qagnn_abi_version(), (unsigned long)qagnn_graph_prep_bytes(s.N, s.E),
+         (unsigned long)pl.total_bytes, (unsigned long)qagnn_fold_bytes(&s));
+  return qagnn_mp_forward(&s, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == QAGNN_ERR_INVALID_ARGUMENT ? 0 : 1;
+}
+''')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "caller"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                         str(src), "-o", str(exe), "-L", libdir, "-lqagnn_b200", f"-Wl,-rpath,{libdir}"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    ver, prep_bytes, total, fold = (int(x) for x in run.stdout.split())
+    s = _lib.Shape(64000, 320000, 200, 4, 4, 38, 5, 200)
+    assert ver == 3 and prep_bytes == total == lib.qagnn_graph_prep_bytes(64000, 320000) and fold == lib.qagnn_fold_bytes(C.byref(s))
