@@ -202,3 +202,25 @@ def test_prefetching_generator_reraises_worker_errors(tmp_path):
     next(it)
     with pytest.raises(IndexError):
         next(it)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flat_cache_pack_on_ragged_and_empty_graphs(seed):
+    """Random nested adjacency with empty sub-graphs (and, for seed 0, no edges at all): pack == pack_adj of the slice."""
+    g = torch.Generator().manual_seed(seed)
+    n, nc, Q = 17, 3, 7
+    sizes = torch.randint(0, 9, (Q, nc), generator=g)
+    if seed == 0:
+        sizes.zero_()
+    sizes[2] = 0                                            # one question whose choices all have empty graphs
+    ei = [[torch.randint(0, n, (2, int(sizes[q, c])), generator=g) for c in range(nc)] for q in range(Q)]
+    et = [[torch.randint(0, 38, (int(sizes[q, c]),), generator=g) for c in range(nc)] for q in range(Q)]
+    flat = Dt.FlatAdjCache.from_nested(ei, et, n)
+    assert flat.n_graphs() == Q * nc and int(flat.graph_ptr[-1]) == int(sizes.sum())
+    for idx in ([0], [2], [6, 2, 1], list(range(Q)), [3, 3]):
+        want = Dt.pack_adj([ei[i] for i in idx], [et[i] for i in idx], n, pin=False)
+        got = flat.pack(idx, pin=False)
+        assert torch.equal(got.edge_index, want.edge_index) and torch.equal(got.edge_type, want.edge_type)
+        assert torch.equal(got.graph_ptr, want.graph_ptr) and got.edge_index.dtype == torch.long
+    sub = flat[1:4]
+    assert torch.equal(sub.pack([1], pin=False).graph_ptr, flat.pack([2], pin=False).graph_ptr)
