@@ -83,10 +83,18 @@ def load():
     if _lib is not None:
         return _lib
     from . import build as _build
-    if os.path.exists(LIB_PATH) and not _build.is_current():
-        # sources changed since the library was built: rebuild when a compiler is around, never run stale code.  Under
-        # torchrun every rank gets here at once: one rebuilds under an exclusive file lock, the others wait and re-check.
+    if not _build.is_current():
+        # library missing (fresh checkout: built artefacts are not in the history) or older than qagnn_b200/csrc: build it
+        # when a compiler is around, never run stale code.  Under torchrun every rank gets here at once: one builds under an
+        # exclusive file lock, the others wait and re-check.
         import fcntl
+        stale = os.path.exists(LIB_PATH)
+        try:
+            _build._nvcc()
+        except RuntimeError:
+            raise RuntimeError(
+                f"{LIB_PATH} is {'older than qagnn_b200/csrc' if stale else 'missing'} and there is no nvcc to build it. Run "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` on a machine with the CUDA toolkit. There is no CPU fallback.") from None
         os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
         with open(LIB_PATH + ".lock", "w") as lock:
             fcntl.flock(lock, fcntl.LOCK_EX)
@@ -94,13 +102,12 @@ def load():
                 if not _build.is_current():
                     _build.build()
             except Exception as e:  # noqa: BLE001
-                raise RuntimeError(f"{LIB_PATH} is older than qagnn_b200/csrc and could not be rebuilt: {e}") from e
+                raise RuntimeError(f"{LIB_PATH} is {'older than qagnn_b200/csrc' if stale else 'missing'} and could not be "
+                                   f"built: {e}. There is no CPU fallback.") from e
             finally:
                 fcntl.flock(lock, fcntl.LOCK_UN)
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"{LIB_PATH} is missing: the qagnn_b200 CUDA library has not been built. Run "
-            f"`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
+        raise RuntimeError(f"{LIB_PATH} is missing after a build. There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

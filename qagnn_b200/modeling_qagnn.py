@@ -11,8 +11,10 @@ own parameters and device buffers (PyTorch = memory + streams).
     QAGNN                    <- modeling/modeling_qagnn.py:99-189   (caller side, plain PyTorch)
     LM_QAGNN                 <- modeling/modeling_qagnn.py:192-251  (caller side, plain PyTorch)
 
-Scope: eval-mode forward (dropout = identity, BatchNorm running statistics) — the reference's
-`evaluate_accuracy` path (qagnn.py:30-38).  Training mode raises; there is no CPU fallback.
+Modes: `.eval()` = the fused inference forward (dropout = identity, BatchNorm running statistics folded into the
+weights) — the reference's `evaluate_accuracy` path (qagnn.py:30-38); `.train()` = dropout, BatchNorm batch statistics
+and autograd through the CUDA message-passing forward / backward kernels (qagnn_b200/training.py; qagnn.py:249-278).
+CPU tensors raise: there is no CPU fallback.
 """
 import ctypes as C
 
