@@ -189,3 +189,21 @@ int main(void) {
     ver, prep_bytes, total, fold = (int(x) for x in run.stdout.split())
     s = _lib.Shape(64000, 320000, 200, 4, 4, 38, 5, 200)
     assert ver == 3 and prep_bytes == total == lib.qagnn_graph_prep_bytes(64000, 320000) and fold == lib.qagnn_fold_bytes(C.byref(s))
+
+
+def test_loader_fails_loudly_without_library_and_compiler(monkeypatch, tmp_path):
+    """No CPU fallback: with the library missing and no nvcc, load() raises (it builds only when a compiler is present)."""
+    from qagnn_b200 import build
+
+    def no_nvcc():
+        raise RuntimeError("nvcc not found")
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "lib" / "libqagnn_b200.so"))
+    monkeypatch.setattr(build, "is_current", lambda: False)
+    monkeypatch.setattr(build, "_nvcc", no_nvcc)
+    with pytest.raises(RuntimeError, match="missing and there is no nvcc.*no CPU fallback"):
+        _lib.load()
+    mod = qagnn_b200.QAGNN_Message_Passing(None, 1, 4, 38, 16, 16, 16).eval()
+    with pytest.raises(RuntimeError):   # CPU tensors never reach a fallback either
+        mod(torch.zeros(1, 2, 16), (torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, dtype=torch.long)),
+            torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2, 1))
