@@ -2,7 +2,8 @@
 
 Run in the build container only (needs /root/reference):
 
-    python -m oracle.make_goldens
+    python -m oracle.make_goldens            # writes tests/golden/*.pt
+    python -m oracle.make_goldens --check    # re-mints in memory, compares with the committed files, writes nothing
 
 Every fixture is produced by the unmodified `GATConvE` / `QAGNN_Message_Passing` / `QAGNN`
 classes of /root/reference/modeling/modeling_qagnn.py (imported through oracle/ref_shim.py),
@@ -12,6 +13,7 @@ case description, a fingerprint of the regenerated inputs, and the reference out
 """
 import hashlib
 import os
+import sys
 
 import torch
 
@@ -284,30 +286,58 @@ def mint_train_decoder_case(ref, case, n_ntype=4, n_etype=38):
             "input_fp": fingerprint(inp["H"], inp["edge_index"], sent_vecs, concept_ids)}
 
 
+def _max_diff(a, b, path=""):
+    """Largest absolute difference between two fixtures (nested dicts / lists of tensors and scalars); raises on a
+    structural mismatch."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and a.keys() == b.keys(), f"{path}: keys differ"
+        return max([_max_diff(a[k_], b[k_], f"{path}.{k_}") for k_ in a] or [0.0])
+    if isinstance(a, (list, tuple)):
+        assert isinstance(b, (list, tuple)) and len(a) == len(b), f"{path}: lengths differ"
+        return max([_max_diff(x, y, f"{path}[{i}]") for i, (x, y) in enumerate(zip(a, b))] or [0.0])
+    if torch.is_tensor(a):
+        assert torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype, f"{path}: tensor meta differs"
+        return float((a.double() - b.double()).abs().max()) if a.numel() else 0.0
+    if isinstance(a, float):
+        return abs(a - b)
+    assert a == b, f"{path}: {a!r} != {b!r}"
+    return 0.0
+
+
+def all_cases():
+    return ([(mint_mp_case, c) for c in MP_CASES] + [(mint_layer_case, c) for c in LAYER_CASES] +
+            [(mint_train_case, c) for c in TRAIN_CASES] + [(mint_train_decoder_case, c) for c in TRAIN_DEC_CASES] +
+            [(mint_decoder_case, c) for c in DEC_CASES])
+
+
+def check(names=None):
+    """Re-mints every fixture (or those in `names`) from the reference in memory and returns {name: max |diff|} against the
+    committed file — nothing is written.  0.0 everywhere = the fixtures are what the reference's own modules produce here."""
+    torch.set_num_threads(8)
+    ref = load_reference()
+    out = {}
+    for mint, case in all_cases():
+        if names is not None and case["name"] not in names:
+            continue
+        have = torch.load(os.path.join(GOLDEN_DIR, case["name"] + ".pt"), weights_only=False)
+        out[case["name"]] = _max_diff(mint(ref, case), have, case["name"])
+    return out
+
+
 def main():
+    if "--check" in sys.argv[1:]:
+        worst = 0.0
+        for name, diff in check().items():
+            print(f"{name}: max |re-minted - committed| = {diff:.3g}")
+            worst = max(worst, diff)
+        sys.exit(0 if worst == 0.0 else 1)
     torch.set_num_threads(8)
     ref = load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for case in MP_CASES:
-        fx = mint_mp_case(ref, case)
+    for mint, case in all_cases():
+        fx = mint(ref, case)
         torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
-        print("minted", case["name"], tuple(fx["out"].shape), float(fx["out"].abs().mean()))
-    for case in LAYER_CASES:
-        fx = mint_layer_case(ref, case)
-        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
-        print("minted", case["name"], tuple(fx["out"].shape), float(fx["out"].abs().mean()))
-    for case in TRAIN_CASES:
-        fx = mint_train_case(ref, case)
-        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
-        print("minted", case["name"], fx["loss"], float(fx["grad_H"].abs().mean()))
-    for case in TRAIN_DEC_CASES:
-        fx = mint_train_decoder_case(ref, case)
-        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
-        print("minted", case["name"], fx["loss"])
-    for case in DEC_CASES:
-        fx = mint_decoder_case(ref, case)
-        torch.save(fx, os.path.join(GOLDEN_DIR, case["name"] + ".pt"))
-        print("minted", case["name"], tuple(fx["logits"].shape), fx["logits"].flatten()[:4].tolist())
+        print("minted", case["name"], fx.get("kind"))
 
 
 if __name__ == "__main__":

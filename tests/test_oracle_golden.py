@@ -75,3 +75,21 @@ def test_state_dict_contract():
     sd = O.random_state_dict(2, 64)
     assert sorted(sd.keys()) == keys
     assert "gnn_layers.1.edge_encoder.3.weight" in keys and "edge_encoder.3.weight" in keys
+
+
+def test_committed_goldens_are_what_the_reference_produces_here():
+    """Build container only (needs /root/reference): re-mint every fixture in memory from the reference's own modules and
+    require it to equal the committed file bit for bit (`python -m oracle.make_goldens --check`, writes nothing)."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/modeling"):
+        pytest.skip("the reference tree is not on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.make_goldens", "--check"], cwd=root, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if "max |re-minted - committed|" in l]
+    import glob
+    assert len(lines) == len(glob.glob(os.path.join(root, "tests", "golden", "*.pt"))) >= 20
+    assert all(l.endswith("= 0") for l in lines)
