@@ -4,6 +4,7 @@ Run in the build container only (needs /root/reference):
 
     python -m oracle.make_goldens            # writes tests/golden/*.pt
     python -m oracle.make_goldens --check    # re-mints in memory, compares with the committed files, writes nothing
+    python -m oracle.make_goldens --fuzz 24  # reference vs oracle on 24 random cases that are not committed as fixtures
 
 Every fixture is produced by the unmodified `GATConvE` / `QAGNN_Message_Passing` / `QAGNN`
 classes of /root/reference/modeling/modeling_qagnn.py (imported through oracle/ref_shim.py),
@@ -324,7 +325,41 @@ def check(names=None):
     return out
 
 
+def fuzz(count, tol_abs=2e-6, tol_rel=2e-5):
+    """Random small cases that are NOT committed as fixtures: the reference's own QAGNN_Message_Passing against the oracle
+    (output, node_feature_extra, first / last layer x and attention, edge_index').  Returns [(case, worst excess over the
+    tolerance)]; excess <= 0 means inside `tol_abs + tol_rel*|ref|`."""
+    torch.set_num_threads(8)
+    ref = load_reference()
+    g = torch.Generator().manual_seed(12345)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))  # noqa: E731
+    results = []
+    for i in range(count):
+        n = ri(1, 30)
+        R = (38, 38, 6, 17)[ri(0, 3)]
+        case = dict(name=f"fuzz{i}", B=ri(1, 4), n=n, e=ri(0, 80), D=(16, 32, 64, 100)[ri(0, 3)], k=ri(1, 3),
+                    regime=("prod", "peaky")[ri(0, 1)], realistic=bool(ri(0, 1)) and n >= 8 and R >= 6, seed=100 + i)
+        fx = mint_mp_case(ref, case, 4, R)
+        inp = O.synth_graph_batch(case["B"], case["n"], case["e"], case["D"], R, case["seed"], case["realistic"])
+        sd = O.random_state_dict(case["k"], case["D"], 4, R, case["regime"], case["seed"])
+        out, extra, layers = O.message_passing_forward(sd, inp["H"], inp["edge_index"], inp["edge_type"], inp["node_type"],
+                                                       inp["node_score"], case["k"], 4, R, return_layers=True)
+        pairs = [(out, fx["out"]), (extra, fx["extra"])]
+        for l, want in fx["layers"].items():
+            pairs += [(layers[l]["x"], want["x"]), (layers[l]["alpha"], want["alpha"])]
+        worst = max(float(((a - b).abs() - tol_abs - tol_rel * b.abs()).max()) if a.numel() else -tol_abs for a, b in pairs)
+        results.append((dict(case, n_etype=R), worst))
+    return results
+
+
 def main():
+    if "--fuzz" in sys.argv[1:]:
+        count = int(sys.argv[sys.argv.index("--fuzz") + 1])
+        bad = 0
+        for case, worst in fuzz(count):
+            print(f"{case}: {'inside' if worst <= 0 else 'OUTSIDE'} the tolerance (excess {worst:.3g})")
+            bad += worst > 0
+        sys.exit(1 if bad else 0)
     if "--check" in sys.argv[1:]:
         worst = 0.0
         for name, diff in check().items():
